@@ -1,0 +1,49 @@
+"""Build recipe for libdfq_sm100.so (hand-written sm_100a CUDA behind a C ABI).
+
+The library is built IN-TREE next to this file so that it travels with the repository snapshot to the
+GPU box; it is git-ignored.  nvcc cross-compiles for sm_100a without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdfq_sm100.so")
+SOURCES = ["tensor_ops.cu", "cle_engine.cu", "passes.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dfq_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--fmad=false",          # every fp32 op of the reference is individually rounded: never contract
+    "-Xcompiler", "-fPIC", "-shared",
+    "-Xptxas", "-v",
+]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libdfq_sm100.so")
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,151 @@
+// Shared device/host helpers for libdfq_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+
+#include "../../include/dfq_b200.h"
+
+namespace dfq {
+
+// ------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define DFQ_CUDA(call)                                                     \
+  do {                                                                     \
+    cudaError_t _e = (call);                                               \
+    if (_e != cudaSuccess) return ::dfq::cuda_fail(_e, #call);             \
+  } while (0)
+
+#define DFQ_REQUIRE(cond, msg)                                             \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      ::dfq::set_error("%s (%s)", msg, #cond);                             \
+      return DFQ_E_ARG;                                                    \
+    }                                                                      \
+  } while (0)
+
+// Stream-ordered device copy of a small host table; freed with free_async on the same stream.
+template <typename T>
+int upload(const T* host, int64_t n, T** dev, cudaStream_t st) {
+  *dev = nullptr;
+  if (n <= 0) return 0;
+  DFQ_CUDA(cudaMallocAsync((void**)dev, sizeof(T) * n, st));
+  DFQ_CUDA(cudaMemcpyAsync(*dev, host, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+inline void free_async(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+
+int sm_count();
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#define DFQ_INF __int_as_float(0x7f800000)
+
+// 128-bit global accesses.  Weights are read once and written once per pass, and inside the
+// persistent kernels they are re-read in a later phase after OTHER SMs rewrote them: every access to
+// mutable arena data therefore bypasses the (non-coherent) L1 with .cg and is served by L2.
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_stream1(float* p, float v) {
+  asm volatile("st.global.cg.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// float atomic min/max through the integer ordering of IEEE bit patterns (works in global and shared).
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v));
+  else          atomicMax((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));
+  else          atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+
+__device__ __forceinline__ float ld_volatile_f(const float* p) {
+  return *(const volatile float*)p;
+}
+
+// Scalar prologue of UniformQuantize.forward (utils/quantize.py:49-66) in double, as Python does it.
+struct QuantScalars {
+  float neg_min;   // fp32(-min_value)       operand of add_(-min_value)
+  float min_v;     // fp32(min_value)        operand of the final add_(min_value)
+  float scale;     // fp32(scale)            operand of div_/mul_
+  float inv_scale; // 1.0f / fp32(scale)     reciprocal-multiply mode (PyTorch CUDA eager)
+  float qmin, qmax;
+};
+__host__ __device__ inline QuantScalars quant_scalars(double mn, double mx, int num_bits, int symmetric) {
+  QuantScalars q;
+  double qmin, qmax, scale;
+  if (symmetric) {
+    qmin = -ldexp(1.0, num_bits - 1);
+    qmax = ldexp(1.0, num_bits - 1) - 1.0;
+    mx = fabs(mx);
+    mn = fabs(mn);
+    if (mx < mn) mx = mn;
+    scale = mx / qmax;
+    mn = 0.0;
+  } else {
+    qmin = 0.0;
+    qmax = ldexp(1.0, num_bits) - 1.0;
+    scale = (mx - mn) / (qmax - qmin);
+  }
+  // Python max(scale, 1e-8): 1e-8 only if 1e-8 > scale (a NaN scale stays NaN)
+  if (1e-8 > scale) scale = 1e-8;
+  q.neg_min = (float)(-mn);
+  q.min_v = (float)mn;
+  q.scale = (float)scale;
+  q.inv_scale = 1.0f / q.scale;
+  q.qmin = (float)qmin;
+  q.qmax = (float)qmax;
+  return q;
+}
+
+// quantize.py:70-74, one element.  Every op is individually rounded (no FMA contraction).
+template <bool RECIP>
+__device__ __forceinline__ float fake_quant(float x, const QuantScalars& q, float* code = nullptr) {
+  float t = __fadd_rn(x, q.neg_min);
+  t = RECIP ? __fmul_rn(t, q.inv_scale) : __fdiv_rn(t, q.scale);
+  t = fminf(fmaxf(t, q.qmin), q.qmax);
+  t = rintf(t);
+  if (code) *code = t;
+  t = __fmul_rn(t, q.scale);
+  return __fadd_rn(t, q.min_v);
+}
+
+}  // namespace dfq

@@ -1,0 +1,347 @@
+"""Host side of the calibration engine: arena planning, descriptor tables, C-ABI calls.
+
+A :class:`Session` owns one fp32 device *arena* holding every weight, bias and per-channel vector of
+the layers being calibrated, plus the scratch the kernels need.  Host logic (graph walks, which layer
+pairs with which) produces small descriptor tables; all arithmetic happens in libdfq_sm100.so.
+
+The session is the object behind the drop-in functions of :mod:`dfq_b200.dfq` and
+:mod:`dfq_b200.utils.layer_transform`; it can also be driven directly (bench.py, tests) with tensors
+that already live on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DfqError
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class CleResult:
+    n_sweeps: int
+    converged: bool
+    last_diff: float
+    diffs: List[float]
+
+
+@dataclass
+class _Bound:
+    off: int
+    n: int
+    tensor: Optional[torch.Tensor]   # host/device tensor mirrored at [off, off+n); None = scratch
+    writeback: bool = True
+
+
+class Session:
+    """One arena + its descriptor tables.  Not thread-safe; one CUDA device."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._n = 0
+        self._bound: List[_Bound] = []
+        self._layers: List[dict] = []
+        self.arena: Optional[torch.Tensor] = None
+        self._staging: Optional[torch.Tensor] = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---- arena planning ---------------------------------------------------------------------------
+    def alloc(self, n: int, align: int = 4) -> int:
+        """Reserve n floats of scratch; returns the float offset."""
+        assert self.arena is None or self._n + n + align <= self.arena.numel(), "arena already materialised"
+        off = _round_up(self._n, align)
+        self._n = off + int(n)
+        return off
+
+    def bind(self, t: torch.Tensor, writeback: bool = True) -> int:
+        """Mirror tensor `t` (fp32, any device) in the arena; returns its offset."""
+        if t.dtype != torch.float32:
+            raise DfqError("calibration tensors must be float32, got %s" % t.dtype)
+        off = self.alloc(t.numel())
+        self._bound.append(_Bound(off, t.numel(), t, writeback))
+        return off
+
+    def add_layer(self, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> int:
+        """Register a Conv2d ([O,J,k,k]) or Linear ([O,J]) weight and its bias (None -> zeros scratch)."""
+        if weight.dim() not in (2, 4):
+            raise DfqError("target layer weight must be 2-D or 4-D, got %s" % (tuple(weight.shape),))
+        rows, cols = int(weight.shape[0]), int(weight.shape[1])
+        kk = int(weight.numel() // (rows * cols))
+        w_off = self.bind(weight)
+        if bias is not None:
+            b_off = self.bind(bias)
+        else:
+            b_off = self.alloc(rows)
+        self._layers.append(dict(w_off=w_off, bias_off=b_off, rows=rows, cols=cols, kk=kk, has_bias=bias is not None))
+        return len(self._layers) - 1
+
+    def layer(self, li: int) -> dict:
+        return self._layers[li]
+
+    def attach_bias(self, li: int, bias: torch.Tensor):
+        """Bind a (new, zero) bias tensor to the scratch bias of layer li so it is written back."""
+        l = self._layers[li]
+        assert not l["has_bias"] and bias.numel() == l["rows"]
+        self._bound.append(_Bound(l["bias_off"], l["rows"], bias, True))
+        l["has_bias"] = True
+
+    # ---- materialise / move data --------------------------------------------------------------------
+    def materialize(self, extra_floats: int = 0):
+        """Allocate the device arena (zero-filled) sized for everything planned so far (+extra)."""
+        if self.arena is not None:
+            return
+        total = _round_up(self._n + extra_floats + 4, 4)
+        self.arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+
+    def _ensure_room(self):
+        if self.arena is None:
+            self.materialize()
+        elif self._n > self.arena.numel():
+            grown = torch.zeros(_round_up(self._n + 4, 4), dtype=torch.float32, device=self.device)
+            grown[: self.arena.numel()].copy_(self.arena)
+            self.arena = grown
+
+    def upload(self):
+        """Copy every bound tensor into the arena: host tensors through ONE pinned staging buffer and
+        one H2D copy, device tensors with device-to-device copies."""
+        self._ensure_room()
+        host = [b for b in self._bound if b.tensor is not None and not b.tensor.is_cuda]
+        if host:
+            lo = min(b.off for b in host)
+            hi = max(b.off + b.n for b in host)
+            if self._staging is None or self._staging.numel() < hi - lo:
+                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=True)
+            st = self._staging
+            # regions between bound tensors carry scratch that must keep its device value: copy only the
+            # bound ranges, coalescing adjacent ones
+            host.sort(key=lambda b: b.off)
+            for b in host:
+                st[b.off - lo: b.off - lo + b.n].copy_(b.tensor.detach().reshape(-1))
+            runs = []
+            for b in host:
+                if runs and _round_up(runs[-1][1], 4) >= b.off and not self._scratch_between(runs[-1][1], b.off):
+                    runs[-1][1] = b.off + b.n
+                else:
+                    runs.append([b.off, b.off + b.n])
+            for a, e in runs:
+                self.arena[a:e].copy_(st[a - lo: e - lo], non_blocking=True)
+                self.h2d_bytes += 4 * (e - a)
+        for b in self._bound:
+            if b.tensor is not None and b.tensor.is_cuda:
+                self.arena[b.off: b.off + b.n].copy_(b.tensor.detach().reshape(-1))
+
+    def _scratch_between(self, a: int, b: int) -> bool:
+        return b - a >= 4   # only alignment padding (<4 floats) may be overwritten by a coalesced run
+
+    def download(self):
+        """Write every bound tensor (writeback=True) back into its original storage, in place."""
+        host = [b for b in self._bound if b.tensor is not None and b.writeback and not b.tensor.is_cuda]
+        if host:
+            lo = min(b.off for b in host)
+            hi = max(b.off + b.n for b in host)
+            if self._staging is None or self._staging.numel() < hi - lo:
+                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=True)
+            st = self._staging
+            st[: hi - lo].copy_(self.arena[lo:hi], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.d2h_bytes += 4 * (hi - lo)
+            with torch.no_grad():
+                for b in host:
+                    b.tensor.detach().reshape(-1).copy_(st[b.off - lo: b.off - lo + b.n]) if b.tensor.is_contiguous() \
+                        else b.tensor.detach().copy_(st[b.off - lo: b.off - lo + b.n].reshape(b.tensor.shape))
+        with torch.no_grad():
+            for b in self._bound:
+                if b.tensor is not None and b.writeback and b.tensor.is_cuda:
+                    b.tensor.detach().copy_(self.arena[b.off: b.off + b.n].reshape(b.tensor.shape))
+
+    def view(self, off: int, n: int) -> torch.Tensor:
+        return self.arena[off: off + n]
+
+    # ---- tables ------------------------------------------------------------------------------------
+    def _layer_table(self, roles: Optional[Dict[int, dict]] = None) -> np.ndarray:
+        t = np.zeros(len(self._layers), dtype=_lib.LAYER_DT)
+        for i, l in enumerate(self._layers):
+            t[i]["w_off"] = l["w_off"]; t[i]["bias_off"] = l["bias_off"]
+            t[i]["rows"] = l["rows"]; t[i]["cols"] = l["cols"]; t[i]["kk"] = l["kk"]
+            t[i]["rel_in"] = -1; t[i]["rel_out"] = -1; t[i]["col_mode"] = 0
+            t[i]["cmin_off"] = -1; t[i]["cmax_off"] = -1
+            if roles and i in roles:
+                for k, v in roles[i].items():
+                    t[i][k] = v
+        return t
+
+    def _ptr(self):
+        return C.c_void_p(self.arena.data_ptr())
+
+    # ---- BN fold --------------------------------------------------------------------------------------
+    def run_bn_fold(self, folds: Sequence[dict]):
+        """folds: dicts(layer, bn_eps, gamma_off, beta_off, mean_off, var_off, fake_w_off, fake_b_off)."""
+        if not folds:
+            return
+        self._ensure_room()
+        ft = np.zeros(len(folds), dtype=_lib.FOLD_DT)
+        for i, f in enumerate(folds):
+            for k in ft.dtype.names:
+                ft[i][k] = f[k]
+        lt = self._layer_table()
+        _lib.check(self.lib.dfq_bn_fold(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
+                                        _lib.table_ptr(ft), len(ft), _lib.stream_ptr()), "dfq_bn_fold")
+
+    # ---- cross-layer equalization -----------------------------------------------------------------
+    def run_cle(self, relations: Sequence[Tuple[int, int, int, int]], s_range=(1e-8, 1e8), converge_thres=2e-7,
+                converge_count=20, signed=False, eps=0, max_sweeps=0) -> Tuple[CleResult, List[int]]:
+        """relations: (first_layer, second_layer, bn_w_off | -1, bn_b_off | -1) in processing order.
+
+        Returns (result, [s_acc offsets]) - s_acc[i] holds Relation.S of relation i ([rows(first)]).
+        Mirrors dfq.py:78-117; see include/dfq_b200.h dfq_cle_run for the contract.
+        """
+        nR = len(relations)
+        if nR == 0:
+            return CleResult(0, True, 10.0, []), []
+        rel_in: Dict[int, int] = {}
+        rel_out: Dict[int, int] = {}
+        for i, (a, b, _, _) in enumerate(relations):
+            if a in rel_out or b in rel_in:
+                raise DfqError("a layer may be `first` of one relation and `second` of one relation only")
+            rel_out[a] = i
+            rel_in[b] = i
+        for l in set(rel_in) & set(rel_out):
+            if rel_in[l] > rel_out[l]:
+                raise DfqError("relations must be in forward chain order (as utils.relation.create_relation emits)")
+        rt = np.zeros(nR, dtype=_lib.RELATION_DT)
+        s_offs = []
+        roles: Dict[int, dict] = {}
+        for i, (a, b, bnw, bnb) in enumerate(relations):
+            la, lb = self._layers[a], self._layers[b]
+            C1, J2 = la["rows"], lb["cols"]
+            G = 1 if C1 == J2 else C1 // J2                      # dfq.py:29-32
+            if G < 1 or G * J2 != C1 or lb["rows"] % G != 0:
+                raise DfqError("unsupported relation shapes: first rows %d, second [%d, %d]" % (C1, lb["rows"], J2))
+            r = rt[i]
+            r["first"] = a; r["second"] = b; r["channels"] = C1; r["groups"] = G
+            r["gi"] = C1 // G; r["go"] = lb["rows"] // G
+            r["bn_w_off"] = bnw; r["bn_b_off"] = bnb
+            r["s_acc_off"] = self.alloc(C1); r["s_step_off"] = self.alloc(C1); r["inv_off"] = self.alloc(C1)
+            s_offs.append(int(r["s_acc_off"]))
+            roles.setdefault(a, {})["rel_out"] = i
+            rb = roles.setdefault(b, {})
+            rb["rel_in"] = i
+            rb["cmin_off"] = self.alloc(2 * C1); rb["cmax_off"] = self.alloc(2 * C1)
+        for l, ro in roles.items():
+            if "rel_in" in ro:
+                if "rel_out" not in ro:
+                    ro["col_mode"] = 0
+                elif self._layers[l]["cols"] == 1 and rt[ro["rel_in"]]["go"] == 1:
+                    ro["col_mode"] = 1
+                else:
+                    ro["col_mode"] = 2
+        # chain position of every layer -> steps
+        pos: Dict[int, int] = {}
+        for i, (a, b, _, _) in enumerate(relations):      # forward order guarantees pos[a] is known
+            if a not in pos:
+                pos[a] = 0
+            pos[b] = pos[a] + 1
+        n_steps = max(pos.values()) + 1
+        buckets: List[List[int]] = [[] for _ in range(n_steps)]
+        for l in sorted(pos):
+            buckets[pos[l]].append(l)
+        step_ptr = np.zeros(n_steps + 1, dtype=np.int32)
+        for p in range(n_steps):
+            step_ptr[p + 1] = step_ptr[p] + len(buckets[p])
+        step_layers = np.array([l for b in buckets for l in b], dtype=np.int32)
+
+        self._ensure_room()
+        lt = self._layer_table(roles)
+        lo, hi = float(s_range[0]), float(s_range[1])
+        P = np.zeros(1, dtype=_lib.CLE_PARAMS_DT)
+        P[0]["s_lo"] = np.float32(lo); P[0]["s_hi"] = np.float32(hi)
+        with np.errstate(divide="ignore"):
+            P[0]["inv_lo"] = np.float32(np.float64(1.0) / np.float64(lo)) if lo != 0 else np.float32(np.inf)
+            P[0]["inv_hi"] = np.float32(np.float64(1.0) / np.float64(hi)) if hi != 0 else np.float32(np.inf)
+        P[0]["eps"] = np.float32(eps); P[0]["signed_mode"] = 1 if signed else 0
+        P[0]["converge_thres"] = float(converge_thres); P[0]["converge_count"] = int(converge_count)
+        P[0]["max_sweeps"] = int(max_sweeps)
+        R = np.zeros(1, dtype=_lib.CLE_RESULT_DT)
+        _lib.check(self.lib.dfq_cle_run(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
+                                        _lib.table_ptr(rt), nR, _lib.table_ptr(step_ptr), _lib.table_ptr(step_layers),
+                                        n_steps, _lib.table_ptr(P), _lib.table_ptr(R), _lib.stream_ptr()), "dfq_cle_run")
+        n = int(R[0]["n_sweeps"])
+        res = CleResult(n, bool(R[0]["converged"]), float(R[0]["last_diff"]), [float(x) for x in R[0]["diffs"][:min(n, 64)]])
+        return res, s_offs
+
+    # ---- bias correction ----------------------------------------------------------------------------
+    def run_bias_correct(self, items: Sequence[dict], num_bits: int = 8):
+        """items (in graph order): dict(layer, signed, terms=[dict(bn_w_off, bn_b_off, n, relu, op)], next_bn_b_off,
+        level) with op in {'set', 'cat', 'add'}.  Returns the list of delta offsets ([rows] each)."""
+        if not items:
+            return []
+        bt = np.zeros(len(items), dtype=_lib.BC_LAYER_DT)
+        terms = []
+        order = sorted(range(len(items)), key=lambda i: (items[i]["level"], i))
+        delta_offs = [0] * len(items)
+        levels = []
+        for slot, i in enumerate(order):
+            it = items[i]
+            l = self._layers[it["layer"]]
+            b = bt[slot]
+            b["layer"] = it["layer"]; b["signed_mode"] = 1 if it.get("signed") else 0
+            b["term_begin"] = len(terms)
+            length = 0
+            for k, t in enumerate(it["terms"]):
+                op = t["op"] if k else "set"
+                if op in ("set", "cat"):
+                    dst, acc = length, 0
+                    length += t["n"]
+                else:
+                    if t["n"] != length:
+                        raise DfqError("bias correction: summed expectations differ in length (%d vs %d)" % (t["n"], length))
+                    dst, acc = 0, 1
+                terms.append((t["bn_w_off"], t["bn_b_off"], t["n"], 1 if t["relu"] else 0, dst, acc))
+            b["term_end"] = len(terms)
+            if length == 0 or length % l["cols"] != 0:
+                raise DfqError("bias correction: expectation length %d incompatible with %d input channels" % (length, l["cols"]))
+            b["expect_len"] = length
+            b["expect_off"] = self.alloc(length)
+            b["delta_off"] = self.alloc(l["rows"])
+            b["minmax_off"] = self.alloc(2)
+            b["next_bn_b_off"] = it.get("next_bn_b_off", -1)
+            delta_offs[i] = int(b["delta_off"])
+            levels.append(it["level"])
+        tt = np.zeros(max(1, len(terms)), dtype=_lib.TERM_DT)
+        for k, t in enumerate(terms):
+            tt[k] = t
+        uniq = sorted(set(levels))
+        level_ptr = np.zeros(len(uniq) + 1, dtype=np.int32)
+        for k, lv in enumerate(uniq):
+            level_ptr[k + 1] = level_ptr[k] + sum(1 for x in levels if x == lv)
+        self._ensure_room()
+        lt = self._layer_table()
+        _lib.check(self.lib.dfq_bias_correct(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
+                                             _lib.table_ptr(bt), len(bt), _lib.table_ptr(tt), len(terms),
+                                             _lib.table_ptr(level_ptr), len(uniq), int(num_bits), _lib.stream_ptr()),
+                   "dfq_bias_correct")
+        return delta_offs
+
+    # ---- weight / bias fake quantization ---------------------------------------------------------
+    def run_quantize(self, tasks: Sequence[Tuple[int, int, int, bool]]):
+        """tasks: (offset, n, num_bits, symmetric); per-tensor min/max then in-place fake-quant."""
+        if not tasks:
+            return
+        qt = np.zeros(len(tasks), dtype=_lib.QUANT_TASK_DT)
+        for i, (off, n, bits, sym) in enumerate(tasks):
+            qt[i]["off"] = off; qt[i]["n"] = n; qt[i]["num_bits"] = bits; qt[i]["symmetric"] = 1 if sym else 0
+            qt[i]["minmax_off"] = self.alloc(2)
+        self._ensure_room()
+        _lib.check(self.lib.dfq_quantize_tensors(self._ptr(), self.arena.numel(), _lib.table_ptr(qt), len(qt),
+                                                 _lib.stream_ptr()), "dfq_quantize_tensors")

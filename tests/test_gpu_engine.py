@@ -1,0 +1,217 @@
+"""-m gpu parity tests of the arena engine (libdfq_sm100.so through dfq_b200.engine.Session) against
+the numpy oracle on seeded inputs.  Equalization, BN fold factors and fake-quant are compared
+bit-exactly; bias correction to 1e-5 normwise (fp32 mat-vec has no defined order in the reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dfq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, gain=True):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(*shape, generator=g)
+    if gain:
+        w = w * (10 ** torch.empty(shape[0]).uniform_(-1, 1, generator=g)).view(-1, *([1] * (len(shape) - 1)))
+    return w.contiguous()
+
+
+def _normwise(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+PAIRS = [
+    ((32, 16, 3, 3), (24, 32, 3, 3)),      # dense -> dense, short rows (warp path, kk=9 columns)
+    ((32, 3, 3, 3), (32, 1, 3, 3)),        # dense(27, unaligned rows) -> depthwise  (G = 32)
+    ((48, 1, 3, 3), (16, 48, 1, 1)),       # depthwise -> pointwise
+    ((96, 16, 1, 1), (96, 1, 3, 3)),       # pointwise -> depthwise
+    ((64, 32, 1, 1), (10, 64)),            # pointwise -> linear
+    ((32, 8, 3, 3), (24, 16, 3, 3)),       # grouped second conv (G = 2)
+    ((64, 128, 3, 3), (48, 64, 3, 3)),     # rows of 1152 floats: CTA-per-row path
+    ((40, 512, 3, 3), (24, 40, 3, 3)),     # rows of 4608 floats
+    ((8, 2500, 1, 1), (12, 8, 1, 1)),      # rows of 2500 floats (cta vec path, partial)
+    ((6, 9001), (5, 6)),                   # row longer than the register tile: generic path, odd length
+    ((7, 33, 1, 1), (9, 7, 1, 1)),         # scalar path, 33 elements
+]
+
+
+@pytest.mark.parametrize("s1,s2", PAIRS)
+@pytest.mark.parametrize("signed", [False, True])
+def test_single_relation_matches_oracle(s1, s2, signed):
+    from dfq_b200.engine import Session
+    w1, w2 = _mk(s1, 1), _mk(s2, 2, gain=False)
+    C1 = s1[0]
+    g = torch.Generator().manual_seed(3)
+    b1 = torch.randn(C1, generator=g); bw = torch.rand(C1, generator=g) + 0.5; bb = torch.randn(C1, generator=g)
+    n = [t.clone().numpy() for t in (w1, w2, b1, bw, bb)]
+    S_ref = O.layer_equalization(*n, signed=signed)
+
+    sess = Session()
+    l1 = sess.add_layer(w1, b1); l2 = sess.add_layer(w2, None)
+    obw, obb = sess.bind(bw), sess.bind(bb)
+    sess.upload()
+    res, s_offs = sess.run_cle([(l1, l2, obw, obb)], signed=signed, max_sweeps=1)
+    S = sess.view(s_offs[0], C1).cpu().numpy()
+    sess.download()
+    assert res.n_sweeps == 1
+    for name, got, ref in (("S", S, S_ref), ("w1", w1.numpy(), n[0]), ("w2", w2.numpy(), n[1]), ("b1", b1.numpy(), n[2]),
+                           ("bn_w", bw.numpy(), n[3]), ("bn_b", bb.numpy(), n[4])):
+        assert np.array_equal(got, ref), "%s differs: normwise %g" % (name, _normwise(got, ref))
+
+
+def test_degenerate_channels_and_clamp():
+    from dfq_b200.engine import Session
+    for s_range in ((1e-8, 1e8), (0.5, 2.0), (1 / 3.0, 3.0)):
+        w1, w2 = _mk((32, 16, 3, 3), 5), _mk((24, 32, 3, 3), 6, gain=False)
+        w1[1] = 0; w1[3] = 0.5
+        w2.view(24, 32, -1)[:, 2] = 0
+        b1 = torch.randn(32)
+        n = [w1.clone().numpy(), w2.clone().numpy(), b1.clone().numpy()]
+        S_ref = O.layer_equalization(n[0], n[1], n[2], None, None, s_range=s_range)
+        sess = Session()
+        l1 = sess.add_layer(w1, b1); l2 = sess.add_layer(w2, None)
+        sess.upload()
+        res, s_offs = sess.run_cle([(l1, l2, -1, -1)], s_range=s_range, max_sweeps=1)
+        S = sess.view(s_offs[0], 32).cpu().numpy()
+        sess.download()
+        assert np.array_equal(S, S_ref)
+        assert np.array_equal(w1.numpy(), n[0], equal_nan=True)
+        assert np.array_equal(w2.numpy(), n[1], equal_nan=True)
+        assert np.array_equal(b1.numpy(), n[2])
+
+
+def _chain_case(shapes, seed):
+    ws = [_mk(s, seed + i, gain=(i % 2 == 0)) for i, s in enumerate(shapes)]
+    g = torch.Generator().manual_seed(seed + 100)
+    bs = [torch.randn(s[0], generator=g) for s in shapes]
+    bns = [(torch.rand(s[0], generator=g) + 0.5, torch.randn(s[0], generator=g)) for s in shapes[:-1]]
+    return ws, bs, bns
+
+
+CHAINS = [
+    [(32, 3, 3, 3), (32, 1, 3, 3), (16, 32, 1, 1), (96, 16, 1, 1), (96, 1, 3, 3), (24, 96, 1, 1)],   # MobileNetV2 chain 1
+    [(144, 24, 1, 1), (144, 1, 3, 3), (32, 144, 1, 1)],                                               # inverted residual
+    [(64, 32, 3, 3), (64, 64, 3, 3), (48, 64, 3, 3), (10, 48)],                                       # dense chain: re-scanned middles
+    [(16, 8, 3, 3), (32, 8, 3, 3), (32, 1, 3, 3), (20, 32, 1, 1)],                                    # grouped (G=2) then depthwise
+]
+
+
+@pytest.mark.parametrize("shapes", CHAINS)
+@pytest.mark.parametrize("signed", [False, True])
+def test_chain_to_convergence_matches_oracle(shapes, signed):
+    """Several chains at once, run to the reference's exit rule: sweep count, every weight, bias, BN
+    vector and accumulated S must equal the oracle bit for bit."""
+    from dfq_b200.engine import Session
+    ws, bs, bns = _chain_case(shapes, 11)
+    # a second, independent chain (isolated pair) shares the sweep loop, as in a real model
+    xw = [_mk((48, 24, 3, 3), 77), _mk((40, 48, 3, 3), 78, gain=False)]
+    xb = [torch.randn(48), torch.randn(40)]
+    xbn = (torch.rand(48) + 0.5, torch.randn(48))
+
+    layers = [O.OLayer(w.clone().numpy(), b.clone().numpy()) for w, b in zip(ws + xw, bs + xb)]
+    obns = [(a.clone().numpy(), b.clone().numpy()) for a, b in bns + [xbn]]
+    nl = len(ws)
+    rels = [O.ORelation(i, i + 1, i) for i in range(nl - 1)] + [O.ORelation(nl, nl + 1, nl - 1)]
+    n_ref, diffs_ref = O.cross_layer_equalization(layers, obns, rels, signed=signed)
+
+    sess = Session()
+    ids = [sess.add_layer(w, b) for w, b in zip(ws + xw, bs + xb)]
+    bn_offs = [(sess.bind(a), sess.bind(b)) for a, b in bns + [xbn]]
+    sess.upload()
+    rl = [(ids[i], ids[i + 1], bn_offs[i][0], bn_offs[i][1]) for i in range(nl - 1)]
+    rl.append((ids[nl], ids[nl + 1], bn_offs[nl - 1][0], bn_offs[nl - 1][1]))
+    res, s_offs = sess.run_cle(rl, signed=signed)
+    S = [sess.view(o, sess.layer(r[0])["rows"]).cpu().numpy() for o, r in zip(s_offs, rl)]
+    sess.download()
+
+    assert res.n_sweeps == n_ref, (res.n_sweeps, n_ref, res.diffs[:5], diffs_ref[:5])
+    assert res.converged
+    np.testing.assert_allclose(res.diffs[:len(diffs_ref)][:64], diffs_ref[:64], rtol=1e-6, atol=1e-12)
+    for i, (w, b) in enumerate(zip(ws + xw, bs + xb)):
+        assert np.array_equal(w.numpy(), layers[i].w), "weight %d normwise %g" % (i, _normwise(w.numpy(), layers[i].w))
+        assert np.array_equal(b.numpy(), layers[i].b), "bias %d" % i
+    for i, (a, b) in enumerate(bns + [xbn]):
+        assert np.array_equal(a.numpy(), obns[i][0]) and np.array_equal(b.numpy(), obns[i][1])
+    for i, r in enumerate(rels):
+        assert np.array_equal(S[i], r.S), "S of relation %d" % i
+
+
+def test_bn_fold_matches_oracle():
+    from dfq_b200.engine import Session
+    sess = Session()
+    cases = []
+    for i, shape in enumerate([(32, 16, 3, 3), (24, 1, 3, 3), (40, 512, 3, 3), (10, 64), (7, 33, 1, 1)]):
+        g = torch.Generator().manual_seed(40 + i)
+        w = torch.randn(*shape, generator=g); b = torch.randn(shape[0], generator=g) if i % 2 == 0 else None
+        gamma = torch.randn(shape[0], generator=g); beta = torch.randn(shape[0], generator=g)
+        mean = torch.randn(shape[0], generator=g); var = torch.rand(shape[0], generator=g) + 0.1
+        ref = O.bn_fold(w.numpy().copy(), None if b is None else b.numpy().copy(), gamma.numpy(), beta.numpy(), mean.numpy(),
+                        var.numpy(), 1e-5)
+        li = sess.add_layer(w, b)
+        offs = dict(layer=li, bn_eps=1e-5, gamma_off=sess.bind(gamma, False), beta_off=sess.bind(beta, False),
+                    mean_off=sess.bind(mean, False), var_off=sess.bind(var, False),
+                    fake_w_off=sess.alloc(shape[0]), fake_b_off=sess.alloc(shape[0]))
+        cases.append((w, b, li, offs, ref))
+    sess.upload()
+    sess.run_bn_fold([c[3] for c in cases])
+    out = [(sess.view(sess.layer(c[2])["bias_off"], c[0].shape[0]).cpu().numpy(),
+            sess.view(c[3]["fake_w_off"], c[0].shape[0]).cpu().numpy(),
+            sess.view(c[3]["fake_b_off"], c[0].shape[0]).cpu().numpy()) for c in cases]
+    sess.download()
+    for (w, b, li, offs, ref), (bias, fw, fb) in zip(cases, out):
+        assert np.array_equal(w.numpy(), ref[0])
+        assert np.array_equal(bias, ref[1])
+        assert np.array_equal(fw, ref[2]) and np.array_equal(fb, ref[3])
+
+
+@pytest.mark.parametrize("bits,sym", [(8, False), (8, True), (4, False), (16, False), (16, True)])
+def test_quantize_tensors_bit_exact(bits, sym):
+    from dfq_b200.engine import Session
+    sess = Session()
+    ts = [torch.randn(64, 32, 3, 3) * 3, torch.randn(1001), torch.randn(10, 1280) * 0.1, torch.full((17,), 0.25), torch.randn(3)]
+    refs = [O.quantize(t.numpy(), bits, float(t.min()), float(t.max()), symmetric=sym) for t in ts]
+    offs = [sess.bind(t) for t in ts]
+    sess.upload()
+    sess.run_quantize([(o, t.numel(), bits, sym) for o, t in zip(offs, ts)])
+    sess.download()
+    for t, r in zip(ts, refs):
+        assert np.array_equal(t.numpy(), r.reshape(t.shape))
+
+
+def test_bias_correct_chain_matches_oracle():
+    """conv1+BN1+ReLU -> conv2+BN2 -> conv3 (no ReLU between 2 and 3): two corrected layers in series; the second
+    one reads the fake_bias the first one just updated."""
+    from dfq_b200.engine import Session
+    g = torch.Generator().manual_seed(9)
+    w2 = torch.randn(48, 32, 3, 3, generator=g) * 0.1; b2 = torch.randn(48, generator=g)
+    w3 = torch.randn(20, 48, 1, 1, generator=g) * 0.2
+    bn1 = (torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.3)
+    bn2 = (torch.rand(48, generator=g) + 0.5, torch.randn(48, generator=g) * 0.3)
+    # oracle
+    e1 = O.relu_expectation(bn1[0].numpy(), bn1[1].numpy())
+    d2 = O.bias_delta(w2.numpy(), e1)
+    b2_ref = b2.numpy() + (-d2)
+    fb2 = bn2[1].numpy() + (-d2)
+    e2 = fb2                                  # no ReLU after BN2
+    d3 = O.bias_delta(w3.numpy(), e2)
+    b3_ref = np.zeros(20, np.float32) + (-d3)
+
+    sess = Session()
+    l2 = sess.add_layer(w2, b2); l3 = sess.add_layer(w3, None)
+    o1 = (sess.bind(bn1[0]), sess.bind(bn1[1])); o2 = (sess.bind(bn2[0]), sess.bind(bn2[1]))
+    sess.upload()
+    items = [dict(layer=l2, signed=False, level=0, next_bn_b_off=o2[1],
+                  terms=[dict(bn_w_off=o1[0], bn_b_off=o1[1], n=32, relu=True, op="set")]),
+             dict(layer=l3, signed=False, level=1, next_bn_b_off=-1,
+                  terms=[dict(bn_w_off=o2[0], bn_b_off=o2[1], n=48, relu=False, op="set")])]
+    doffs = sess.run_bias_correct(items)
+    d2_gpu = sess.view(doffs[0], 48).cpu().numpy(); d3_gpu = sess.view(doffs[1], 20).cpu().numpy()
+    b3_gpu = sess.view(sess.layer(l3)["bias_off"], 20).cpu().numpy()
+    sess.download()
+    assert _normwise(d2_gpu, d2) < 1e-5 and _normwise(d3_gpu, d3) < 1e-5
+    assert _normwise(b2.numpy(), b2_ref) < 1e-5
+    assert _normwise(bn2[1].numpy(), fb2) < 1e-5
+    assert _normwise(b3_gpu, b3_ref) < 1e-5
