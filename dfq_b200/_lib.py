@@ -60,7 +60,7 @@ TERM_DT = np.dtype([
 
 BC_LAYER_DT = np.dtype([
     ("layer", np.int32), ("signed_mode", np.int32), ("term_begin", np.int32), ("term_end", np.int32),
-    ("expect_len", np.int32),
+    ("expect_len", np.int32), ("flags", np.int32),
     ("expect_off", np.int64), ("delta_off", np.int64), ("next_bn_b_off", np.int64), ("minmax_off", np.int64),
 ], align=True)
 
@@ -90,12 +90,12 @@ SIGNATURES = {
                     C.c_void_p, C.c_void_p, _ST],
     "dfq_bn_fold": [_PF, _I64, C.c_void_p, _I32, C.c_void_p, _I32, _ST],
     "dfq_bias_correct": [_PF, _I64, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, _I32, _I32, _ST],
-    "dfq_quantize_tensors": [_PF, _I64, C.c_void_p, _I32, _ST],
+    "dfq_quantize_tensors": [_PF, _I64, C.c_void_p, _I32, C.c_int, _ST],
     "dfq_minmax": [_PF, _I64, _PF, _ST],
     "dfq_quant_dequant": [_PF, _PF, _I64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _PF, _ST],
-    "dfq_quant_dequant_dev": [_PF, _PF, _I64, _PF, C.c_int, C.c_int, C.c_int, _PF, _ST],
+    "dfq_quant_dequant_dev": [_PF, _PF, _I64, _PF, _PF, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _ST],
     "dfq_act_minmax_per_sample": [_PF, _I64, _I64, _PF, _PF, _ST],
-    "dfq_observer_update": [_PF, _PF, C.c_int, C.c_float, _ST],
+    "dfq_observer_update": [_PF, _PF, _PF, C.c_int, C.c_float, _ST],
     "dfq_range_rows": [_PF, _I64, _I64, _PF, _PF, _ST],
     "dfq_range_cols": [_PF, _I64, _I64, _I64, _I64, _PF, _PF, _ST],
     "dfq_mean_abs_diff": [_PF, _PF, _I64, C.c_void_p, _ST],

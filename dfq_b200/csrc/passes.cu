@@ -141,6 +141,7 @@ k_minmax_tasks(float* arena, const FlatTask* __restrict__ T, int nT) {
   }
 }
 
+template <bool RECIP>
 __global__ void __launch_bounds__(kThreads)
 k_quant_tasks(float* arena, const FlatTask* __restrict__ T, int nT) {
   long long base = 0;
@@ -160,13 +161,13 @@ k_quant_tasks(float* arena, const FlatTask* __restrict__ T, int nT) {
           const int64_t lo4 = lo >> 2, hi4 = hi >> 2;
           for (int64_t i = lo4 + threadIdx.x; i < hi4; i += kThreads) {
             float4 v = ldg_stream(x4 + i);
-            v.x = fake_quant<false>(v.x, q); v.y = fake_quant<false>(v.y, q);
-            v.z = fake_quant<false>(v.z, q); v.w = fake_quant<false>(v.w, q);
+            v.x = fake_quant<RECIP>(v.x, q); v.y = fake_quant<RECIP>(v.y, q);
+            v.z = fake_quant<RECIP>(v.z, q); v.w = fake_quant<RECIP>(v.w, q);
             stg_stream(x4 + i, v);
           }
-          for (int64_t i = (hi4 << 2) + threadIdx.x; i < hi; i += kThreads) stg_stream1(x + i, fake_quant<false>(ldg_stream1(x + i), q));
+          for (int64_t i = (hi4 << 2) + threadIdx.x; i < hi; i += kThreads) stg_stream1(x + i, fake_quant<RECIP>(ldg_stream1(x + i), q));
         } else {
-          for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) stg_stream1(x + i, fake_quant<false>(ldg_stream1(x + i), q));
+          for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) stg_stream1(x + i, fake_quant<RECIP>(ldg_stream1(x + i), q));
         }
       }
     }
@@ -273,9 +274,13 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
             for (int j = tid; j < l.cols; j += tpr) {
               float E = 0.f;
               const float* p = rowp + (size_t)j * l.kk;
-              for (int k = 0; k < l.kk; ++k) {
-                const float w = p[k];
-                E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w));
+              if (b.flags & 1) {          // raw weight sum: bias absorption, dfq.py:150-153
+                for (int k = 0; k < l.kk; ++k) E = __fadd_rn(E, p[k]);
+              } else {
+                for (int k = 0; k < l.kk; ++k) {
+                  const float w = p[k];
+                  E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w));
+                }
               }
               acc += (double)E * (double)__ldcg(ex + j);
             }
@@ -293,7 +298,7 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
           if (leader) {
             const float d = (float)acc;
             __stcg(arena + b.delta_off + o, d);
-            __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), -d));        // dfq.py:292
+            __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), (b.flags & 2) ? d : -d));  // dfq.py:292 / :164
             if (b.next_bn_b_off >= 0)                                                                // dfq.py:204-206,293
               __stcg(arena + b.next_bn_b_off + o, __fadd_rn(__ldcg(arena + b.next_bn_b_off + o), -d));
           }
@@ -343,7 +348,7 @@ extern "C" int dfq_bn_fold(float* arena, int64_t arena_floats, const DfqLayer* l
 }
 
 extern "C" int dfq_quantize_tensors(float* arena, int64_t arena_floats, const DfqQuantTask* tasks, int32_t n_tasks,
-                                    void* stream) {
+                                    int div_mode, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DFQ_REQUIRE(arena && tasks, "null argument");
   if (n_tasks <= 0) return 0;
@@ -362,7 +367,8 @@ extern "C" int dfq_quantize_tensors(float* arena, int64_t arena_floats, const Df
   if ((rc = upload(ft.data(), n_tasks, &dT, st))) return rc;
   k_minmax_init<<<std::min(148, (n_tasks + 255) / 256), 256, 0, st>>>(arena, dT, n_tasks);
   k_minmax_tasks<<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
-  k_quant_tasks<<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
+  if (div_mode) k_quant_tasks<true><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
+  else          k_quant_tasks<false><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
   DFQ_CUDA(cudaGetLastError());
   free_async(dT, st);
   return 0;

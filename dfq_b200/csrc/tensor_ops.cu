@@ -111,27 +111,54 @@ __global__ void k_batch_mean(const float* __restrict__ scratch, int64_t batch, f
   }
 }
 
-__global__ void k_observer_update(float* running2, const float* __restrict__ stat2, int mode, float momentum) {
+__global__ void k_observer_update(float* rmin, float* rmax, const float* __restrict__ stat2, int mode, float momentum) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (mode == 1) {
       // Python min()/max() on 0-d tensors (quantize.py:106-107): the smaller / larger value
-      running2[0] = fminf(running2[0], stat2[0]);
-      running2[1] = fmaxf(running2[1], stat2[1]);
+      rmin[0] = fminf(rmin[0], stat2[0]);
+      rmax[0] = fmaxf(rmax[0], stat2[1]);
     } else {
       // running.mul_(1 - m).add_(value * m) (quantize.py:112-113), separately rounded
       const float om = (float)(1.0 - (double)momentum);
-      running2[0] = __fadd_rn(__fmul_rn(running2[0], om), __fmul_rn(stat2[0], momentum));
-      running2[1] = __fadd_rn(__fmul_rn(running2[1], om), __fmul_rn(stat2[1], momentum));
+      rmin[0] = __fadd_rn(__fmul_rn(rmin[0], om), __fmul_rn(stat2[0], momentum));
+      rmax[0] = __fadd_rn(__fmul_rn(rmax[0], om), __fmul_rn(stat2[1], momentum));
     }
   }
 }
 
+// Scalar prologue when min/max are fp32 0-d TENSORS in the reference (quantize.py:24-35 then :49-66 on
+// tensors): the same formulas evaluated with fp32 tensor ops.  recip = a CUDA tensor divided by a
+// Python scalar is a multiply by the fp32 reciprocal in PyTorch eager.
+__device__ inline QuantScalars quant_scalars_f32(float mn, float mx, int num_bits, int symmetric, bool recip) {
+  QuantScalars q;
+  float scale;
+  if (symmetric) {
+    q.qmin = -ldexpf(1.0f, num_bits - 1);
+    q.qmax = ldexpf(1.0f, num_bits - 1) - 1.0f;
+    mx = fabsf(mx); mn = fabsf(mn);
+    if (mx < mn) mx = mn;
+    scale = recip ? __fmul_rn(mx, __frcp_rn(q.qmax)) : __fdiv_rn(mx, q.qmax);
+    mn = 0.f;
+  } else {
+    q.qmin = 0.f;
+    q.qmax = (float)(ldexp(1.0, num_bits) - 1.0);
+    const float d = __fsub_rn(mx, mn);
+    scale = recip ? __fmul_rn(d, __frcp_rn(q.qmax)) : __fdiv_rn(d, q.qmax);
+  }
+  if (1e-8f > scale) scale = 1e-8f;
+  q.neg_min = -mn; q.min_v = mn; q.scale = scale; q.inv_scale = __frcp_rn(scale);
+  return q;
+}
+
 template <bool RECIP, bool DEV_RANGE, bool ERR>
 __global__ void __launch_bounds__(kThreads)
-k_quant(const float* __restrict__ x, float* __restrict__ y, int64_t n, QuantScalars qs, const float* __restrict__ minmax2,
-        int num_bits, int symmetric, float* __restrict__ codes) {
+k_quant(const float* __restrict__ x, float* __restrict__ y, int64_t n, QuantScalars qs, const float* __restrict__ min_ptr,
+        const float* __restrict__ max_ptr, int num_bits, int symmetric, int prologue, float* __restrict__ codes) {
   QuantScalars q = qs;
-  if (DEV_RANGE) q = quant_scalars((double)minmax2[0], (double)minmax2[1], num_bits, symmetric);
+  if (DEV_RANGE) {
+    if (prologue == 0) q = quant_scalars((double)min_ptr[0], (double)max_ptr[0], num_bits, symmetric);
+    else q = quant_scalars_f32(min_ptr[0], max_ptr[0], num_bits, symmetric, prologue == 2);
+  }
   const int64_t start = blockIdx.x * (int64_t)kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
   const bool al = ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)codes)) & 15) == 0;
   if (al) {
@@ -280,20 +307,25 @@ extern "C" int dfq_quant_dequant(const float* x, float* y, int64_t n, float min_
   QuantScalars q;
   q.neg_min = -min_value; q.min_v = min_value; q.scale = scale; q.inv_scale = 1.0f / scale; q.qmin = qmin; q.qmax = qmax;
   const int grid = flat_grid(n, 8);
-  if (div_mode) k_quant<true, false, false><<<grid, kThreads, 0, st>>>(x, y, n, q, nullptr, 0, 0, codes);
-  else          k_quant<false, false, false><<<grid, kThreads, 0, st>>>(x, y, n, q, nullptr, 0, 0, codes);
+  if (div_mode) k_quant<true, false, false><<<grid, kThreads, 0, st>>>(x, y, n, q, nullptr, nullptr, 0, 0, 0, codes);
+  else          k_quant<false, false, false><<<grid, kThreads, 0, st>>>(x, y, n, q, nullptr, nullptr, 0, 0, 0, codes);
   DFQ_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int dfq_quant_dequant_dev(const float* x, float* y, int64_t n, const float* minmax2, int num_bits,
-                                     int symmetric, int div_mode, float* codes, void* stream) {
+extern "C" int dfq_quant_dequant_dev(const float* x, float* y, int64_t n, const float* min_ptr, const float* max_ptr,
+                                     int num_bits, int symmetric, int div_mode, int prologue, float* codes,
+                                     void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  DFQ_REQUIRE(x && y && minmax2 && n > 0 && num_bits >= 1 && num_bits <= 32, "bad argument");
+  DFQ_REQUIRE(x && y && min_ptr && max_ptr && n > 0 && num_bits >= 1 && num_bits <= 32, "bad argument");
+  DFQ_REQUIRE(prologue >= 0 && prologue <= 2, "prologue must be 0, 1 or 2");
   QuantScalars q{};
   const int grid = flat_grid(n, 8);
-  if (div_mode) k_quant<true, true, false><<<grid, kThreads, 0, st>>>(x, y, n, q, minmax2, num_bits, symmetric, codes);
-  else          k_quant<false, true, false><<<grid, kThreads, 0, st>>>(x, y, n, q, minmax2, num_bits, symmetric, codes);
+  // a tensor divisor (prologue 1/2) is always a true division in PyTorch, on CPU and on CUDA
+  if (div_mode && prologue == 0)
+    k_quant<true, true, false><<<grid, kThreads, 0, st>>>(x, y, n, q, min_ptr, max_ptr, num_bits, symmetric, prologue, codes);
+  else
+    k_quant<false, true, false><<<grid, kThreads, 0, st>>>(x, y, n, q, min_ptr, max_ptr, num_bits, symmetric, prologue, codes);
   DFQ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -303,7 +335,7 @@ extern "C" int dfq_quant_error(const float* w, float* eps, int64_t n, const floa
   cudaStream_t st = (cudaStream_t)stream;
   DFQ_REQUIRE(w && eps && minmax2 && n > 0, "bad argument");
   QuantScalars q{};
-  k_quant<false, true, true><<<flat_grid(n, 8), kThreads, 0, st>>>(w, eps, n, q, minmax2, num_bits, symmetric, nullptr);
+  k_quant<false, true, true><<<flat_grid(n, 8), kThreads, 0, st>>>(w, eps, n, q, minmax2, minmax2 + 1, num_bits, symmetric, 0, nullptr);
   DFQ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -323,9 +355,10 @@ extern "C" int dfq_act_minmax_per_sample(const float* x, int64_t batch, int64_t 
   return 0;
 }
 
-extern "C" int dfq_observer_update(float* running2, const float* stat2, int mode, float momentum, void* stream) {
-  DFQ_REQUIRE(running2 && stat2 && (mode == 1 || mode == 2), "bad argument");
-  k_observer_update<<<1, 32, 0, (cudaStream_t)stream>>>(running2, stat2, mode, momentum);
+extern "C" int dfq_observer_update(float* running_min, float* running_max, const float* stat2, int mode, float momentum,
+                                   void* stream) {
+  DFQ_REQUIRE(running_min && running_max && stat2 && (mode == 1 || mode == 2), "bad argument");
+  k_observer_update<<<1, 32, 0, (cudaStream_t)stream>>>(running_min, running_max, stat2, mode, momentum);
   DFQ_CUDA(cudaGetLastError());
   return 0;
 }

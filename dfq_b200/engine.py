@@ -59,7 +59,6 @@ class Session:
     # ---- arena planning ---------------------------------------------------------------------------
     def alloc(self, n: int, align: int = 4) -> int:
         """Reserve n floats of scratch; returns the float offset."""
-        assert self.arena is None or self._n + n + align <= self.arena.numel(), "arena already materialised"
         off = _round_up(self._n, align)
         self._n = off + int(n)
         return off
@@ -72,13 +71,13 @@ class Session:
         self._bound.append(_Bound(off, t.numel(), t, writeback))
         return off
 
-    def add_layer(self, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> int:
+    def add_layer(self, weight: torch.Tensor, bias: Optional[torch.Tensor], weight_writeback: bool = True) -> int:
         """Register a Conv2d ([O,J,k,k]) or Linear ([O,J]) weight and its bias (None -> zeros scratch)."""
         if weight.dim() not in (2, 4):
             raise DfqError("target layer weight must be 2-D or 4-D, got %s" % (tuple(weight.shape),))
         rows, cols = int(weight.shape[0]), int(weight.shape[1])
         kk = int(weight.numel() // (rows * cols))
-        w_off = self.bind(weight)
+        w_off = self.bind(weight, weight_writeback)
         if bias is not None:
             b_off = self.bind(bias)
         else:
@@ -296,6 +295,7 @@ class Session:
             l = self._layers[it["layer"]]
             b = bt[slot]
             b["layer"] = it["layer"]; b["signed_mode"] = 1 if it.get("signed") else 0
+            b["flags"] = (1 if it.get("raw_sum") else 0) | (2 if it.get("add") else 0)
             b["term_begin"] = len(terms)
             length = 0
             for k, t in enumerate(it["terms"]):
@@ -334,8 +334,10 @@ class Session:
         return delta_offs
 
     # ---- weight / bias fake quantization ---------------------------------------------------------
-    def run_quantize(self, tasks: Sequence[Tuple[int, int, int, bool]]):
-        """tasks: (offset, n, num_bits, symmetric); per-tensor min/max then in-place fake-quant."""
+    def run_quantize(self, tasks: Sequence[Tuple[int, int, int, bool]], div_mode: int = 0):
+        """tasks: (offset, n, num_bits, symmetric); per-tensor min/max then in-place fake-quant.
+        div_mode 0 = true division (what the reference computes on CPU-resident parameters), 1 = multiply by
+        the fp32 reciprocal (what PyTorch CUDA eager computes)."""
         if not tasks:
             return
         qt = np.zeros(len(tasks), dtype=_lib.QUANT_TASK_DT)
@@ -344,4 +346,4 @@ class Session:
             qt[i]["minmax_off"] = self.alloc(2)
         self._ensure_room()
         _lib.check(self.lib.dfq_quantize_tensors(self._ptr(), self.arena.numel(), _lib.table_ptr(qt), len(qt),
-                                                 _lib.stream_ptr()), "dfq_quantize_tensors")
+                                                 int(div_mode), _lib.stream_ptr()), "dfq_quantize_tensors")

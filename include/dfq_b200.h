@@ -158,6 +158,9 @@ typedef struct DfqBcLayer {
   int32_t signed_mode;       /* symmetric quantizer (dfq.py:218) */
   int32_t term_begin, term_end;  /* into terms[] */
   int32_t expect_len;        /* = groups * cols */
+  int32_t flags;             /* bit 0: use sum_k W instead of the quantization error (bias absorption,
+                                dfq.py:139-153); bit 1: ADD delta to the bias (dfq.py:164) instead of
+                                subtracting it (dfq.py:292) */
   int64_t expect_off;        /* scratch [expect_len] */
   int64_t delta_off;         /* scratch/out [rows]: eps . E[x]                           */
   int64_t next_bn_b_off;     /* fake_bias that receives -delta (dfq.py:204-206), or -1  */
@@ -177,6 +180,7 @@ typedef struct DfqQuantTask {
   int64_t minmax_off;   /* scratch [2] */
 } DfqQuantTask;
 int dfq_quantize_tensors(float* arena, int64_t arena_floats, const DfqQuantTask* tasks, int32_t n_tasks,
+                         int div_mode /* 0: true division (CPU-resident params), 1: reciprocal (CUDA) */,
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -194,21 +198,29 @@ int dfq_minmax(const float* x, int64_t n, float* out2, void* stream);
 int dfq_quant_dequant(const float* x, float* y, int64_t n, float min_value, float scale,
                       float qmin, float qmax, int div_mode, float* codes, void* stream);
 
-/* Same with the range taken from device memory (minmax2 = {min, max}, e.g. written by dfq_minmax or
- * the observer) and the scalar prologue of quantize.py:49-66 evaluated in double on the device:
- * no host synchronisation (replaces the float() syncs of quantize.py:119,195-196). */
-int dfq_quant_dequant_dev(const float* x, float* y, int64_t n, const float* minmax2, int num_bits,
-                          int symmetric, int div_mode, float* codes, void* stream);
+/* Same with the range taken from device memory (*min_ptr, *max_ptr: e.g. the two halves of a dfq_minmax
+ * result, or QuantMeasure's running_min / running_max buffers) and the scalar prologue of
+ * quantize.py:49-66 evaluated on the device: no host synchronisation (replaces the float() syncs of
+ * quantize.py:119,195-196).
+ *   prologue 0: min/max widened to double, scale formed in double (the reference passed float(min),
+ *               float(max): quantize.py:119,195-196, layer_transform.py:289, dfq.py:14)
+ *   prologue 1: min/max are fp32 0-d tensors in the reference (min_value=None, quantize.py:24-35): scale
+ *               formed by fp32 tensor ops, `/ (qmax-qmin)` a true division (CPU tensors)
+ *   prologue 2: as 1 with `/ (qmax-qmin)` a multiply by the fp32 reciprocal (CUDA tensors)
+ * With prologue 1/2 the element-wise division is by a tensor and therefore always a true division. */
+int dfq_quant_dequant_dev(const float* x, float* y, int64_t n, const float* min_ptr, const float* max_ptr,
+                          int num_bits, int symmetric, int div_mode, int prologue, float* codes, void* stream);
 
 /* Observer statistics (quantize.py:106-107,110-111): out2[0] = mean_b min(x[b,:]),
  * out2[1] = mean_b max(x[b,:]) for x viewed as [batch, per_sample]. */
 int dfq_act_minmax_per_sample(const float* x, int64_t batch, int64_t per_sample, float* out2,
                               float* scratch_2b /* [2*batch] */, void* stream);
 
-/* QuantMeasure running statistics update on the device (quantize.py:103-113):
- * mode 1: running = (min(running_min, stat_min), max(running_max, stat_max))    (update_stat)
- * mode 2: running = running*(1-momentum) + stat*momentum                         (training EMA) */
-int dfq_observer_update(float* running2, const float* stat2, int mode, float momentum, void* stream);
+/* QuantMeasure running statistics update on the device (quantize.py:103-113), stat2 = {min, max}:
+ * mode 1: running_min = min(running_min, stat_min), running_max = max(running_max, stat_max)  (update_stat)
+ * mode 2: running = running*(1-momentum) + stat*momentum                                      (training EMA) */
+int dfq_observer_update(float* running_min, float* running_max, const float* stat2, int mode, float momentum,
+                        void* stream);
 
 /* Per-row extrema of a [rows, row_len] matrix (dfq.py:50,54: range of weight_first_group[ii]). */
 int dfq_range_rows(const float* w, int64_t rows, int64_t row_len, float* out_min, float* out_max,
