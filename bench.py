@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the DFQ calibration hot path on B200.
+
+One "step" = one pass of the hot path (BN fold -> cross-layer equalization to convergence -> bias correction) over
+one synthetic stack of independent Conv[512,512,3,3]+BN+ReLU -> Conv[512,512,3,3]+BN blocks (BASELINE.json
+configs[4], the configuration the metric's HBM-roofline half is quoted on; it is the largest single-GPU
+configuration: 4096 layer pairs = 38.65 GB of fp32 weights).  Output: ONE JSON line (see README / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--layers L] [--impl b200|reference]
+
+  value      whole-job Conv/BN layer-pairs per second with the stack resident in HBM (device-timed, CUDA events)
+  e2e        the same metric through the public API with HOST buffers: pinned host -> device, calibrate, device -> host
+  roofline   the dominant kernel (k_cle_engine): algorithmic bytes (8 B per weight per sweep) / its event-timed
+             duration, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (oracle/) timed on the host cores on a bounded sample of the same workload
+
+`--impl reference` times the reference's CPU implementation of the path (its algorithm restated in oracle/, since
+the reference is Python and is not present on the GPU box) on the same workload shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "conv_bn_layer_pairs_equalized_and_corrected_per_second"
+UNIT = "layers/s"
+C, K = 512, 3
+N_PER_LAYER = C * C * K * K
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--layers", type=int, default=4096, help="Conv/BN pairs in the synthetic stack per GPU")
+    p.add_argument("--e2e-layers", type=int, default=256, help="pairs moved host->device->host per e2e step")
+    p.add_argument("--cpu-layers", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--quantize", action="store_true", help="also fake-quantize weights/biases (8 bit) inside the step")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][2]) if self.rows and self.rows[0][2].replace(".", "").isdigit() else None,
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the same workload shape
+# ----------------------------------------------------------------------------------------------------------
+def cpu_pipeline(n_pairs, seed=1234, eager=False):
+    """Time one calibration step (fold -> equalize to convergence -> correct) of `n_pairs` layer pairs on the host.
+    Returns (seconds, sweeps)."""
+    import numpy as np
+    import torch
+    from oracle import dfq_oracle as O
+    if eager:
+        from oracle import eager_port as E
+    n_blocks = max(1, n_pairs // 2)
+    g = torch.Generator().manual_seed(seed)
+    std = (2.0 / (K * K * C)) ** 0.5
+    blocks = []
+    for _ in range(n_blocks):
+        ws = []
+        for _ in range(2):
+            w = torch.randn(C, C, K, K, generator=g) * std
+            w = w * (10 ** torch.empty(C).uniform_(-1, 1, generator=g)).view(-1, 1, 1, 1)
+            bn = [torch.empty(C).uniform_(0.5, 1.5, generator=g), torch.randn(C, generator=g) * 0.2,
+                  torch.randn(C, generator=g) * 0.1, torch.empty(C).uniform_(0.5, 1.5, generator=g)]
+            ws.append((w, bn))
+        blocks.append(ws)
+    t0 = time.perf_counter()
+    sweeps = 0
+    if eager:
+        sweeps = E.calibrate_blocks(blocks)
+    else:
+        layers, bns, rels = [], [], []
+        for ws in blocks:
+            for w, bn in ws:
+                w2, b2, fw, fb = O.bn_fold(w.numpy(), None, *[x.numpy() for x in bn], 1e-5)
+                layers.append(O.OLayer(w2, b2)); bns.append((fw, fb))
+            rels.append(O.ORelation(len(layers) - 2, len(layers) - 1, len(bns) - 2))
+        sweeps, _ = O.cross_layer_equalization(layers, bns, rels)
+        for r in rels:
+            e = O.relu_expectation(*bns[r.bn])
+            d = O.bias_delta(layers[r.second].w, e)
+            layers[r.second].b = layers[r.second].b + (-d)
+            bns[r.second] = (bns[r.second][0], bns[r.second][1] + (-d))
+    return time.perf_counter() - t0, sweeps
+
+
+def run_reference(args, rank, world):
+    import torch
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pairs = args.cpu_layers or 8
+    for _ in range(min(args.warmup, 1)):
+        cpu_pipeline(2, eager=True)
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        dt, sweeps = cpu_pipeline(pairs, eager=True)
+        times.append(dt)
+    dt = sum(times) / len(times)
+    val = pairs / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic stack Conv[512,512,3,3]+BN pairs (BASELINE configs[4])", "layers_per_step": pairs,
+                       "sweeps": sweeps},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d layer pairs per step, PyTorch-eager per-channel port of dfq.py (oracle/eager_port.py)" % pairs},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dfq_b200.engine import Session
+    from dfq_b200.workload import DeviceStack
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    free, total = torch.cuda.mem_get_info()
+    layers = args.layers - (args.layers % 2)
+    bytes_per_layer = 4 * (N_PER_LAYER + 8 * C)
+    while layers > 2 and 2.1 * layers * bytes_per_layer > 0.92 * free:
+        layers //= 2
+    n_blocks = layers // 2
+
+    sess = Session(dev)
+    stack = DeviceStack(sess, n_blocks, C, K, seed=1234 + rank, quantize=args.quantize)
+    stack.generate()
+    pristine = stack.state().clone()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gather_buf = None
+    if world > 1:
+        s_lo = min(stack.cle_plan["s_offs"]); s_hi = max(stack.cle_plan["s_offs"]) + C
+        gather_buf = torch.empty(world * (s_hi - s_lo), dtype=torch.float32, device=dev)
+
+    def step(timers=None):
+        stack.state().copy_(pristine)                       # untimed: restores (and evicts L2: 38 GB >> 126 MB)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        sess.run_bn_fold(stack.fold_plan)
+        ev[1].record()
+        res = sess.run_cle_plan(stack.cle_plan)
+        ev[2].record()
+        sess.run_bias_correct_plan(stack.bc_plan, 8)
+        if stack.quant_plan is not None:
+            sess.run_quantize(stack.quant_plan)
+        ev[3].record()
+        if world > 1:   # the path's one exchange: all-gather of the scale vectors (north_star)
+            dist.all_gather_into_tensor(gather_buf, sess.view(s_lo, s_hi - s_lo))
+        ev[4].record()
+        torch.cuda.synchronize()
+        if timers is not None:
+            timers.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
+        return res
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    timers = []
+    for _ in range(args.steps):
+        res = step(timers)
+    barrier()
+    clocks = sampler.stop()
+
+    t = torch.tensor([sum(sum(r) for r in timers) / len(timers),
+                      sum(r[1] for r in timers) / len(timers)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_cle = float(t[0]), float(t[1])
+    value = world * layers / (ms_step * 1e-3)
+    phases = [sum(r[i] for r in timers) / len(timers) for i in range(4)]
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    cle_bytes = 8.0 * N_PER_LAYER * layers * res.n_sweeps          # 8 B per weight per sweep
+    achieved = cle_bytes / (ms_cle * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_cle_engine", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "algorithmic_bytes_per_launch": cle_bytes, "ms_per_launch": ms_cle,
+                "whole_step": {"algorithmic_bytes": (28.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers,
+                               "GB/s": (28.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers / (ms_step * 1e-3) / 1e9}}
+
+    # ---- end to end with host buffers -----------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e_layers = max(2, min(args.e2e_layers, layers)) // 2 * 2
+        del pristine
+        torch.cuda.empty_cache()
+        sess2 = Session(dev)
+        st2 = DeviceStack(sess2, e_layers // 2, C, K, seed=99 + rank)
+        st2.generate()
+        n_state = st2.state_floats
+        host_in = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
+        host_out = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
+        host_in.copy_(st2.state())
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            st2.state().copy_(host_in, non_blocking=True)
+            st2.run()
+            host_out.copy_(st2.state(), non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * e_layers / (float(tt[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * n_state,
+               "d2h_bytes_per_step": 4 * n_state, "layers_per_step": e_layers, "ms_per_step": float(tt[0]),
+               "api": "dfq_b200.engine.Session / workload.DeviceStack.run over a pinned host image of the stack"}
+
+    if rank != 0:
+        return
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        pairs = args.cpu_layers or 8
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        dt, sw = cpu_pipeline(pairs)
+        cpu = {"value": pairs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d layer pairs, vectorised numpy oracle (oracle/dfq_oracle.py), %d sweeps, %.1f s" % (pairs, sw, dt)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "synthetic stack of %d Conv[512,512,3,3]+BN pairs per GPU (BASELINE configs[4]): "
+                                   "BN fold + equalization to convergence + bias correction%s" % (layers, " + 8-bit fake-quant" if args.quantize else ""),
+                       "layers_per_gpu": layers, "weights_bytes_per_gpu": 4 * N_PER_LAYER * layers, "sweeps": res.n_sweeps,
+                       "parallelism": "independent blocks sharded over %d rank(s); one all-gather of the scale vectors" % world,
+                       "l2": "working set %.1f GB >> 126 MB L2; state restored from a pristine copy (untimed) before every step" % (4e-9 * N_PER_LAYER * layers)},
+            "phases_ms": {"bn_fold": phases[0], "equalize": phases[1], "bias_correct": phases[2], "allgather": phases[3]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": stack.launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

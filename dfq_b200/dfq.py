@@ -21,6 +21,7 @@ from . import _lib
 from .engine import Session
 from .graphwalk import bias_correction_recipe
 from .utils import visualize_per_layer   # noqa: F401  (dfq.py:5 imports it; kept for API parity)
+from .utils import quantize as _Q
 from .utils.quantize import UniformQuantize, tensor_minmax, _ptr  # noqa: F401
 
 
@@ -38,14 +39,13 @@ def _quantize_error(param, num_bits=8, reduction='sum', signed=False):
     lib = _lib.load()
     _lib.require_cuda()
     src = param.detach()
-    dev = src.contiguous() if src.is_cuda else src.contiguous().cuda()
+    dev, _ = _Q._dev_f32(src)
     with torch.no_grad():
         mm = tensor_minmax(dev)
         eps = torch.empty_like(dev)
         # CPU tensors: true division; CUDA tensors: the reference would run div_(float) as a reciprocal multiply
         if src.is_cuda:
-            from .utils.quantize import fake_quant_device_range
-            eps = fake_quant_device_range(dev, num_bits, mm[0:1], mm[1:2], signed, prologue=0, div_mode=1) - dev
+            eps = _Q.fake_quant_device_range(dev, num_bits, mm[0:1], mm[1:2], signed, prologue=0, div_mode=1) - dev
         else:
             _lib.check(lib.dfq_quant_error(_ptr(dev), _ptr(eps), dev.numel(), _ptr(mm), int(num_bits), 1 if signed else 0,
                                            _lib.stream_ptr()), "dfq_quant_error")
@@ -57,7 +57,7 @@ def _quantize_error(param, num_bits=8, reduction='sum', signed=False):
             eps = torch.sum(torch.abs(torch.sum(eps.view(eps.size(0), -1), -1)))
         elif reduction == 'spatial':
             eps = torch.sum(torch.abs(torch.sum(eps.view(eps.size(0), eps.size(1), -1), -1)))
-        return eps if src.is_cuda else eps.cpu()
+        return eps if src.is_cuda else eps.cpu()   # a no-op copy when the tensors are already on the host
 
 
 def _layer_equalization(weight_first, weight_second, bias_first, bn_weight=None, bn_bias=None, s_range=(1e-8, 1e8), signed=False, eps=0):
@@ -163,7 +163,9 @@ def clip_weight(graph, range_clip=[-15, 15], targ_type=[nn.Conv2d, nn.Linear]):
     for idx in graph:
         if type(graph[idx]) in targ_type:
             w = graph[idx].weight.data
-            dev = w.contiguous() if w.is_cuda else w.contiguous().cuda()
+            dev, _ = _Q._dev_f32(w)
+            if dev.data_ptr() == w.data_ptr():
+                dev = dev.clone()
             _lib.check(lib.dfq_clamp(_ptr(dev), dev.numel(), float(range_clip[0]), float(range_clip[1]), _lib.stream_ptr()),
                        "dfq_clamp")
             w.copy_(dev.view(w.shape))

@@ -21,6 +21,13 @@ from . import _lib
 from ._lib import DfqError
 
 
+_PIN = True       # page-locked staging buffers (tests that run the host logic without a GPU turn this off)
+
+
+def _default_device() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _round_up(x: int, a: int) -> int:
     return (x + a - 1) // a * a
 
@@ -47,7 +54,7 @@ class Session:
     def __init__(self, device: Optional[torch.device] = None):
         _lib.require_cuda()
         self.lib = _lib.load()
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device) if device is not None else _default_device()
         self._n = 0
         self._bound: List[_Bound] = []
         self._layers: List[dict] = []
@@ -85,6 +92,13 @@ class Session:
         self._layers.append(dict(w_off=w_off, bias_off=b_off, rows=rows, cols=cols, kk=kk, has_bias=bias is not None))
         return len(self._layers) - 1
 
+    def alloc_layer(self, rows: int, cols: int, kk: int) -> int:
+        """Reserve an (uninitialised, device-only) layer: weight [rows, cols*kk] and bias [rows]."""
+        w_off = self.alloc(rows * cols * kk)
+        b_off = self.alloc(rows)
+        self._layers.append(dict(w_off=w_off, bias_off=b_off, rows=rows, cols=cols, kk=kk, has_bias=False))
+        return len(self._layers) - 1
+
     def layer(self, li: int) -> dict:
         return self._layers[li]
 
@@ -120,7 +134,7 @@ class Session:
             lo = min(b.off for b in host)
             hi = max(b.off + b.n for b in host)
             if self._staging is None or self._staging.numel() < hi - lo:
-                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=True)
+                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=_PIN)
             st = self._staging
             # regions between bound tensors carry scratch that must keep its device value: copy only the
             # bound ranges, coalescing adjacent ones
@@ -150,10 +164,11 @@ class Session:
             lo = min(b.off for b in host)
             hi = max(b.off + b.n for b in host)
             if self._staging is None or self._staging.numel() < hi - lo:
-                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=True)
+                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=_PIN)
             st = self._staging
             st[: hi - lo].copy_(self.arena[lo:hi], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            if self.arena.is_cuda:
+                torch.cuda.current_stream().synchronize()
             self.d2h_bytes += 4 * (hi - lo)
             with torch.no_grad():
                 for b in host:
@@ -184,30 +199,28 @@ class Session:
         return C.c_void_p(self.arena.data_ptr())
 
     # ---- BN fold --------------------------------------------------------------------------------------
-    def run_bn_fold(self, folds: Sequence[dict]):
-        """folds: dicts(layer, bn_eps, gamma_off, beta_off, mean_off, var_off, fake_w_off, fake_b_off)."""
-        if not folds:
-            return
-        self._ensure_room()
+    def plan_bn_fold(self, folds: Sequence[dict]) -> dict:
         ft = np.zeros(len(folds), dtype=_lib.FOLD_DT)
         for i, f in enumerate(folds):
             for k in ft.dtype.names:
                 ft[i][k] = f[k]
-        lt = self._layer_table()
+        return dict(ft=ft, lt=self._layer_table())
+
+    def run_bn_fold(self, folds):
+        """folds: dicts(layer, bn_eps, gamma_off, beta_off, mean_off, var_off, fake_w_off, fake_b_off), or a plan."""
+        plan = folds if isinstance(folds, dict) else (self.plan_bn_fold(folds) if len(folds) else None)
+        if plan is None:
+            return
+        self._ensure_room()
+        ft, lt = plan["ft"], plan["lt"]
         _lib.check(self.lib.dfq_bn_fold(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
                                         _lib.table_ptr(ft), len(ft), _lib.stream_ptr()), "dfq_bn_fold")
 
     # ---- cross-layer equalization -----------------------------------------------------------------
-    def run_cle(self, relations: Sequence[Tuple[int, int, int, int]], s_range=(1e-8, 1e8), converge_thres=2e-7,
-                converge_count=20, signed=False, eps=0, max_sweeps=0) -> Tuple[CleResult, List[int]]:
-        """relations: (first_layer, second_layer, bn_w_off | -1, bn_b_off | -1) in processing order.
-
-        Returns (result, [s_acc offsets]) - s_acc[i] holds Relation.S of relation i ([rows(first)]).
-        Mirrors dfq.py:78-117; see include/dfq_b200.h dfq_cle_run for the contract.
-        """
+    def plan_cle(self, relations: Sequence[Tuple[int, int, int, int]]) -> dict:
+        """Build the descriptor tables + scratch for a list of relations
+        (first_layer, second_layer, bn_w_off | -1, bn_b_off | -1) in processing order (dfq.py:85-86)."""
         nR = len(relations)
-        if nR == 0:
-            return CleResult(0, True, 10.0, []), []
         rel_in: Dict[int, int] = {}
         rel_out: Dict[int, int] = {}
         for i, (a, b, _, _) in enumerate(relations):
@@ -224,7 +237,7 @@ class Session:
         for i, (a, b, bnw, bnb) in enumerate(relations):
             la, lb = self._layers[a], self._layers[b]
             C1, J2 = la["rows"], lb["cols"]
-            G = 1 if C1 == J2 else C1 // J2                      # dfq.py:29-32
+            G = 1 if C1 == J2 else C1 // max(J2, 1)              # dfq.py:29-32
             if G < 1 or G * J2 != C1 or lb["rows"] % G != 0:
                 raise DfqError("unsupported relation shapes: first rows %d, second [%d, %d]" % (C1, lb["rows"], J2))
             r = rt[i]
@@ -245,9 +258,9 @@ class Session:
                     ro["col_mode"] = 1
                 else:
                     ro["col_mode"] = 2
-        # chain position of every layer -> steps
+        # chain position of every layer -> steps (forward order guarantees pos[first] is known)
         pos: Dict[int, int] = {}
-        for i, (a, b, _, _) in enumerate(relations):      # forward order guarantees pos[a] is known
+        for a, b, _, _ in relations:
             if a not in pos:
                 pos[a] = 0
             pos[b] = pos[a] + 1
@@ -258,10 +271,14 @@ class Session:
         step_ptr = np.zeros(n_steps + 1, dtype=np.int32)
         for p in range(n_steps):
             step_ptr[p + 1] = step_ptr[p] + len(buckets[p])
-        step_layers = np.array([l for b in buckets for l in b], dtype=np.int32)
+        step_layers = np.array([l for bk in buckets for l in bk], dtype=np.int32)
+        return dict(rt=rt, lt=self._layer_table(roles), step_ptr=step_ptr, step_layers=step_layers, n_steps=n_steps,
+                    s_offs=s_offs, relations=list(relations))
 
+    def run_cle_plan(self, plan: dict, s_range=(1e-8, 1e8), converge_thres=2e-7, converge_count=20, signed=False,
+                     eps=0, max_sweeps=0) -> CleResult:
+        """Run dfq.py:78-117 on a planned relation list; see include/dfq_b200.h dfq_cle_run."""
         self._ensure_room()
-        lt = self._layer_table(roles)
         lo, hi = float(s_range[0]), float(s_range[1])
         P = np.zeros(1, dtype=_lib.CLE_PARAMS_DT)
         P[0]["s_lo"] = np.float32(lo); P[0]["s_hi"] = np.float32(hi)
@@ -272,19 +289,27 @@ class Session:
         P[0]["converge_thres"] = float(converge_thres); P[0]["converge_count"] = int(converge_count)
         P[0]["max_sweeps"] = int(max_sweeps)
         R = np.zeros(1, dtype=_lib.CLE_RESULT_DT)
+        lt, rt = plan["lt"], plan["rt"]
         _lib.check(self.lib.dfq_cle_run(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
-                                        _lib.table_ptr(rt), nR, _lib.table_ptr(step_ptr), _lib.table_ptr(step_layers),
-                                        n_steps, _lib.table_ptr(P), _lib.table_ptr(R), _lib.stream_ptr()), "dfq_cle_run")
+                                        _lib.table_ptr(rt), len(rt), _lib.table_ptr(plan["step_ptr"]),
+                                        _lib.table_ptr(plan["step_layers"]), plan["n_steps"], _lib.table_ptr(P),
+                                        _lib.table_ptr(R), _lib.stream_ptr()), "dfq_cle_run")
         n = int(R[0]["n_sweeps"])
-        res = CleResult(n, bool(R[0]["converged"]), float(R[0]["last_diff"]), [float(x) for x in R[0]["diffs"][:min(n, 64)]])
-        return res, s_offs
+        return CleResult(n, bool(R[0]["converged"]), float(R[0]["last_diff"]), [float(x) for x in R[0]["diffs"][:min(n, 64)]])
+
+    def run_cle(self, relations: Sequence[Tuple[int, int, int, int]], s_range=(1e-8, 1e8), converge_thres=2e-7,
+                converge_count=20, signed=False, eps=0, max_sweeps=0) -> Tuple[CleResult, List[int]]:
+        """plan_cle + run_cle_plan.  Returns (result, [s_acc offsets]); s_acc[i] holds Relation.S of relation i."""
+        if len(relations) == 0:
+            return CleResult(0, True, 10.0, []), []
+        plan = self.plan_cle(relations)
+        res = self.run_cle_plan(plan, s_range, converge_thres, converge_count, signed, eps, max_sweeps)
+        return res, plan["s_offs"]
 
     # ---- bias correction ----------------------------------------------------------------------------
-    def run_bias_correct(self, items: Sequence[dict], num_bits: int = 8):
+    def plan_bias_correct(self, items: Sequence[dict]) -> dict:
         """items (in graph order): dict(layer, signed, terms=[dict(bn_w_off, bn_b_off, n, relu, op)], next_bn_b_off,
-        level) with op in {'set', 'cat', 'add'}.  Returns the list of delta offsets ([rows] each)."""
-        if not items:
-            return []
+        level[, raw_sum, add]) with op in {'set', 'cat', 'add'}."""
         bt = np.zeros(len(items), dtype=_lib.BC_LAYER_DT)
         terms = []
         order = sorted(range(len(items)), key=lambda i: (items[i]["level"], i))
@@ -325,25 +350,43 @@ class Session:
         level_ptr = np.zeros(len(uniq) + 1, dtype=np.int32)
         for k, lv in enumerate(uniq):
             level_ptr[k + 1] = level_ptr[k] + sum(1 for x in levels if x == lv)
+        return dict(bt=bt, tt=tt, n_terms=len(terms), level_ptr=level_ptr, n_levels=len(uniq), delta_offs=delta_offs,
+                    lt=self._layer_table())
+
+    def run_bias_correct_plan(self, plan: dict, num_bits: int = 8):
         self._ensure_room()
-        lt = self._layer_table()
+        lt, bt, tt = plan["lt"], plan["bt"], plan["tt"]
         _lib.check(self.lib.dfq_bias_correct(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
-                                             _lib.table_ptr(bt), len(bt), _lib.table_ptr(tt), len(terms),
-                                             _lib.table_ptr(level_ptr), len(uniq), int(num_bits), _lib.stream_ptr()),
-                   "dfq_bias_correct")
-        return delta_offs
+                                             _lib.table_ptr(bt), len(bt), _lib.table_ptr(tt), plan["n_terms"],
+                                             _lib.table_ptr(plan["level_ptr"]), plan["n_levels"], int(num_bits),
+                                             _lib.stream_ptr()), "dfq_bias_correct")
+
+    def run_bias_correct(self, items: Sequence[dict], num_bits: int = 8):
+        """plan + run; returns the list of delta offsets ([rows] each), in the order of `items`."""
+        if not items:
+            return []
+        plan = self.plan_bias_correct(items)
+        self.run_bias_correct_plan(plan, num_bits)
+        return plan["delta_offs"]
 
     # ---- weight / bias fake quantization ---------------------------------------------------------
-    def run_quantize(self, tasks: Sequence[Tuple[int, int, int, bool]], div_mode: int = 0):
-        """tasks: (offset, n, num_bits, symmetric); per-tensor min/max then in-place fake-quant.
-        div_mode 0 = true division (what the reference computes on CPU-resident parameters), 1 = multiply by
-        the fp32 reciprocal (what PyTorch CUDA eager computes)."""
-        if not tasks:
-            return
+    def plan_quantize(self, tasks: Sequence[Tuple[int, int, int, bool]]) -> dict:
         qt = np.zeros(len(tasks), dtype=_lib.QUANT_TASK_DT)
         for i, (off, n, bits, sym) in enumerate(tasks):
             qt[i]["off"] = off; qt[i]["n"] = n; qt[i]["num_bits"] = bits; qt[i]["symmetric"] = 1 if sym else 0
             qt[i]["minmax_off"] = self.alloc(2)
+        return dict(qt=qt)
+
+    def run_quantize(self, tasks: Sequence[Tuple[int, int, int, bool]], div_mode: int = 0):
+        """tasks: (offset, n, num_bits, symmetric); per-tensor min/max then in-place fake-quant.
+        div_mode 0 = true division (what the reference computes on CPU-resident parameters), 1 = multiply by
+        the fp32 reciprocal (what PyTorch CUDA eager computes)."""
+        if isinstance(tasks, dict):
+            qt = tasks["qt"]
+        else:
+            if not tasks:
+                return
+            qt = self.plan_quantize(tasks)["qt"]
         self._ensure_room()
         _lib.check(self.lib.dfq_quantize_tensors(self._ptr(), self.arena.numel(), _lib.table_ptr(qt), len(qt),
                                                  int(div_mode), _lib.stream_ptr()), "dfq_quantize_tensors")

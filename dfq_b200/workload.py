@@ -1,0 +1,246 @@
+"""Synthetic workloads of the calibration path: Conv/BN stacks and graph/bottoms dictionaries.
+
+The reference's entry points take a traced model: ``graph`` (OrderedDict key -> nn.Module | op-name string, in
+trace order) and ``bottoms`` (key -> list of input keys), SURVEY.md section 8(b).  On the GPU box neither the
+reference's tracer nor its model files exist, so workloads are described by small *topology* records (node types,
+layer hyper-parameters, edges - facts about the architectures, produced once by ``tools/make_golden.py`` from the
+reference's own trace and committed under ``tests/golden/``) and materialised here with seeded random weights
+("synthetic random Conv/BN weight stacks of the named shapes", BASELINE.json).
+
+Also here: the synthetic stack of BASELINE.json config 5 (independent Conv[C,C,k,k]+BN+ReLU -> Conv[C,C,k,k]+BN
+blocks), generated directly inside a device arena.
+"""
+from __future__ import annotations
+
+import json
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+# ----------------------------------------------------------------------------------------------------
+# topology <-> graph
+# ----------------------------------------------------------------------------------------------------
+_SIMPLE = {"ReLU": nn.ReLU, "ReLU6": nn.ReLU6, "Dropout": nn.Dropout, "Dropout2d": nn.Dropout2d,
+           "Identity": nn.Identity}
+
+
+def describe_module(m) -> Optional[dict]:
+    """Topology record of one traced module (used by tools/make_golden.py)."""
+    t = type(m).__name__
+    if isinstance(m, nn.Conv2d):
+        return dict(type="Conv2d", args=dict(in_channels=m.in_channels, out_channels=m.out_channels,
+                                             kernel_size=list(m.kernel_size), stride=list(m.stride),
+                                             padding=list(m.padding), dilation=list(m.dilation), groups=m.groups,
+                                             bias=m.bias is not None))
+    if isinstance(m, nn.Linear):
+        return dict(type="Linear", args=dict(in_features=m.in_features, out_features=m.out_features, bias=m.bias is not None))
+    if isinstance(m, nn.BatchNorm2d):
+        return dict(type="BatchNorm2d", args=dict(num_features=m.num_features, eps=m.eps))
+    if isinstance(m, nn.AvgPool2d):
+        return dict(type="AvgPool2d", args=dict(kernel_size=m.kernel_size, stride=m.stride, padding=m.padding))
+    if isinstance(m, nn.MaxPool2d):
+        return dict(type="MaxPool2d", args=dict(kernel_size=m.kernel_size, stride=m.stride, padding=m.padding))
+    if isinstance(m, nn.AdaptiveAvgPool2d):
+        return dict(type="AdaptiveAvgPool2d", args=dict(output_size=m.output_size))
+    if t in _SIMPLE:
+        return dict(type=t, args={})
+    return dict(type="Opaque", args=dict(name=t))
+
+
+def _gen(seed: int) -> torch.Generator:
+    return torch.Generator().manual_seed(int(seed))
+
+
+def init_conv_(conv: nn.Conv2d, seed: int, gain_decades: float = 1.0):
+    """He-normal weights (as the reference model files initialise them) times a per-output-channel gain
+    10^U(-g, g) so the channel ranges are imbalanced; bias (if any) ~ N(0, 0.1)."""
+    g = _gen(seed)
+    k = conv.kernel_size[0] * conv.kernel_size[1]
+    std = math.sqrt(2.0 / (k * conv.out_channels))
+    with torch.no_grad():
+        w = torch.randn(conv.weight.shape, generator=g) * std
+        if gain_decades:
+            gain = 10 ** torch.empty(conv.out_channels).uniform_(-gain_decades, gain_decades, generator=g)
+            w = w * gain.view(-1, 1, 1, 1)
+        conv.weight.copy_(w)
+        if conv.bias is not None:
+            conv.bias.copy_(torch.randn(conv.out_channels, generator=g) * 0.1)
+
+
+def init_linear_(lin: nn.Linear, seed: int):
+    g = _gen(seed)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.01)
+        if lin.bias is not None:
+            lin.bias.copy_(torch.randn(lin.out_features, generator=g) * 0.01)
+
+
+def init_bn_(bn: nn.BatchNorm2d, seed: int):
+    """gamma ~ U(0.5, 1.5), beta ~ N(0, 0.2), mean ~ N(0, 0.1), var ~ U(0.5, 1.5)  (SURVEY.md 8d, config 1)."""
+    g = _gen(seed)
+    n = bn.num_features
+    with torch.no_grad():
+        bn.weight.copy_(torch.empty(n).uniform_(0.5, 1.5, generator=g))
+        bn.bias.copy_(torch.randn(n, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+        bn.running_var.copy_(torch.empty(n).uniform_(0.5, 1.5, generator=g))
+
+
+def build_graph(topology: dict, seed: int = 0, conv_cls=nn.Conv2d, linear_cls=nn.Linear,
+                gain_decades: float = 1.0) -> Tuple[OrderedDict, OrderedDict, List[nn.Module]]:
+    """Materialise a topology as (graph, bottoms, modules) with seeded random parameters.
+
+    Module nodes are keyed by ``id(module)`` and functional nodes by their op-name string, exactly like the
+    reference tracer's output; `conv_cls` / `linear_cls` choose the target layer classes (nn.Conv2d or one of the
+    Quant* flavours).
+    """
+    graph, bottoms = OrderedDict(), OrderedDict()
+    key_of: Dict[str, object] = {}
+    modules: List[nn.Module] = []
+    for i, node in enumerate(topology["nodes"]):
+        t, args = node["type"], node.get("args", {})
+        name = node["key"]
+        if t == "Data":
+            key, obj = "Data", "Data"
+        elif t == "Func":
+            key, obj = name, name
+        else:
+            if t == "Conv2d":
+                a = dict(args)
+                for k in ("kernel_size", "stride", "padding", "dilation"):
+                    a[k] = tuple(a[k])
+                obj = conv_cls(**a)
+                init_conv_(obj, seed * 100003 + i, gain_decades)
+            elif t == "Linear":
+                obj = linear_cls(**args)
+                init_linear_(obj, seed * 100003 + i)
+            elif t == "BatchNorm2d":
+                obj = nn.BatchNorm2d(args["num_features"], eps=args.get("eps", 1e-5))
+                init_bn_(obj, seed * 100003 + i)
+            elif t == "AvgPool2d":
+                obj = nn.AvgPool2d(**args)
+            elif t == "MaxPool2d":
+                obj = nn.MaxPool2d(**args)
+            elif t == "AdaptiveAvgPool2d":
+                obj = nn.AdaptiveAvgPool2d(args["output_size"])
+            elif t in _SIMPLE:
+                obj = _SIMPLE[t]()
+            else:
+                obj = nn.Identity()
+            obj.eval()
+            key = id(obj)
+            modules.append(obj)
+        key_of[name] = key
+        graph[key] = obj
+        b = node.get("bottoms")
+        bottoms[key] = None if b is None else [key_of[x] for x in b]
+    return graph, bottoms, modules
+
+
+def load_topology(path: str) -> dict:
+    with open(path) as f:
+        return json.load(f)
+
+
+def stack_topology(n_blocks: int, channels: int = 512, k: int = 3, in_channels: Optional[int] = None) -> dict:
+    """BASELINE.json config 5 as a topology: independent blocks Data -> Conv+BN+ReLU -> Conv+BN (chains of length 1,
+    like ResNet basic blocks).  Every block hangs off 'Data', so the first conv of a block is not bias-corrected
+    (dfq.py:197-198) and the second one is."""
+    ic = in_channels or channels
+    nodes = [dict(key="Data", type="Data", bottoms=None)]
+    for b in range(n_blocks):
+        conv = lambda i, o: dict(in_channels=i, out_channels=o, kernel_size=[k, k], stride=[1, 1], padding=[k // 2, k // 2],
+                                 dilation=[1, 1], groups=1, bias=False)
+        nodes += [
+            dict(key="b%d_conv1" % b, type="Conv2d", args=conv(ic, channels), bottoms=["Data"]),
+            dict(key="b%d_bn1" % b, type="BatchNorm2d", args=dict(num_features=channels, eps=1e-5), bottoms=["b%d_conv1" % b]),
+            dict(key="b%d_relu" % b, type="ReLU", args={}, bottoms=["b%d_bn1" % b]),
+            dict(key="b%d_conv2" % b, type="Conv2d", args=conv(channels, channels), bottoms=["b%d_relu" % b]),
+            dict(key="b%d_bn2" % b, type="BatchNorm2d", args=dict(num_features=channels, eps=1e-5), bottoms=["b%d_conv2" % b]),
+        ]
+    return dict(name="stack_%dx%d_k%d" % (2 * n_blocks, channels, k), input=[1, ic, 8, 8], nodes=nodes)
+
+
+# ----------------------------------------------------------------------------------------------------
+# config 5 directly inside a device arena
+# ----------------------------------------------------------------------------------------------------
+class DeviceStack:
+    """`n_blocks` independent Conv[C,C,k,k]+BN+ReLU -> Conv[C,C,k,k]+BN blocks living only in a Session arena.
+
+    Pipeline per calibration step (the BASELINE metric's unit of work, per Conv/BN pair):
+      BN fold (8N B) -> equalization to convergence (8N B per sweep, 2 sweeps) -> bias correction of the second
+      conv (4N B read twice = 4N B per pair on average) [-> 8-bit weight fake-quant (8N+4N B)]
+    """
+
+    def __init__(self, sess, n_blocks: int, channels: int = 512, k: int = 3, seed: int = 1234, quantize: bool = False):
+        self.sess = sess
+        self.n_blocks, self.C, self.k = n_blocks, channels, k
+        self.n_layers = 2 * n_blocks
+        C, kk = channels, k * k
+        self.N = C * C * kk
+        self.layers = [sess.alloc_layer(C, C, kk) for _ in range(self.n_layers)]
+        self.w_begin = sess.layer(self.layers[0])["w_off"]
+        # per-layer BN vectors: gamma, beta, mean, var, fake_w, fake_b
+        self.vec = [dict((n, sess.alloc(C)) for n in ("gamma", "beta", "mean", "var", "fake_w", "fake_b"))
+                    for _ in range(self.n_layers)]
+        self.vec_begin = self.vec[0]["gamma"]
+        self.vec_end = self.vec[-1]["fake_b"] + C
+        self.seed = seed
+        folds = [dict(layer=li, bn_eps=1e-5, gamma_off=v["gamma"], beta_off=v["beta"], mean_off=v["mean"], var_off=v["var"],
+                      fake_w_off=v["fake_w"], fake_b_off=v["fake_b"]) for li, v in zip(self.layers, self.vec)]
+        self.fold_plan = sess.plan_bn_fold(folds)
+        rels = [(self.layers[2 * b], self.layers[2 * b + 1], self.vec[2 * b]["fake_w"], self.vec[2 * b]["fake_b"])
+                for b in range(n_blocks)]
+        self.cle_plan = sess.plan_cle(rels)
+        items = [dict(layer=self.layers[2 * b + 1], signed=False, level=0, next_bn_b_off=self.vec[2 * b + 1]["fake_b"],
+                      terms=[dict(bn_w_off=self.vec[2 * b]["fake_w"], bn_b_off=self.vec[2 * b]["fake_b"], n=C, relu=True, op="set")])
+                 for b in range(n_blocks)]
+        self.bc_plan = sess.plan_bias_correct(items)
+        self.quant_plan = None
+        if quantize:
+            tasks = []
+            for li in self.layers:
+                l = sess.layer(li)
+                tasks.append((l["w_off"], self.N, 8, False))
+                tasks.append((l["bias_off"], C, 8, False))
+            self.quant_plan = sess.plan_quantize(tasks)
+        sess.materialize()
+        self.state_floats = self.vec_end - self.w_begin
+
+    def generate(self, chunk_layers: int = 64):
+        """Seeded random weights/BN statistics written straight into the arena (device RNG)."""
+        sess, C, kk = self.sess, self.C, self.k * self.k
+        g = torch.Generator(device=sess.device).manual_seed(self.seed)
+        std = math.sqrt(2.0 / (kk * C))
+        for i, (li, v) in enumerate(zip(self.layers, self.vec)):
+            l = sess.layer(li)
+            w = sess.view(l["w_off"], self.N).view(C, C * kk)
+            w.normal_(0.0, std, generator=g)
+            gain = 10 ** torch.empty(C, device=sess.device).uniform_(-1.0, 1.0, generator=g)
+            w.mul_(gain.view(-1, 1))
+            sess.view(l["bias_off"], C).zero_()
+            sess.view(v["gamma"], C).uniform_(0.5, 1.5, generator=g)
+            sess.view(v["beta"], C).normal_(0.0, 0.2, generator=g)
+            sess.view(v["mean"], C).normal_(0.0, 0.1, generator=g)
+            sess.view(v["var"], C).uniform_(0.5, 1.5, generator=g)
+
+    def state(self) -> torch.Tensor:
+        """The mutable region (weights, biases, BN vectors) as one flat view - what a step reads and writes."""
+        return self.sess.view(self.w_begin, self.state_floats)
+
+    def run(self, converge_thres=2e-7):
+        """One calibration step over the whole stack; returns the CleResult."""
+        s = self.sess
+        s.run_bn_fold(self.fold_plan)
+        res = s.run_cle_plan(self.cle_plan, converge_thres=converge_thres)
+        s.run_bias_correct_plan(self.bc_plan, 8)
+        if self.quant_plan is not None:
+            s.run_quantize(self.quant_plan)
+        return res
+
+    @property
+    def launches_per_step(self) -> int:
+        return 3 + (3 if self.quant_plan is not None else 0)

@@ -1,0 +1,66 @@
+"""The C-ABI library builds, loads without a GPU and exports exactly what include/dfq_b200.h declares."""
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "dfq_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from dfq_b200 import _build, _lib
+    _build.build()
+    lib = _lib.load(build_if_missing=False)
+    names = _declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "libdfq_sm100.so does not export %s" % n
+    # and the binding covers every declared function (dfq_last_error is bound separately)
+    for n in names:
+        assert n in _lib.SIGNATURES or n == "dfq_last_error", "dfq_b200/_lib.py has no signature for %s" % n
+    assert lib.dfq_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_mirrors_match_compiled_sizes():
+    from dfq_b200 import _lib
+    lib = _lib.load()
+    for i, (name, (dt, size)) in enumerate(_lib.EXPECTED_SIZES.items()):
+        assert dt.itemsize == size, name
+        assert lib.dfq_struct_size(i) == size, name
+    assert lib.dfq_struct_size(99) == -1
+
+
+def test_struct_field_offsets_follow_the_header_order():
+    """numpy's aligned layout must equal the C layout: check a few load-bearing offsets."""
+    from dfq_b200 import _lib
+    assert _lib.LAYER_DT.fields["rows"][1] == 16 and _lib.LAYER_DT.fields["cmin_off"][1] == 40
+    assert _lib.RELATION_DT.fields["bn_w_off"][1] == 24 and _lib.RELATION_DT.fields["inv_off"][1] == 56
+    assert _lib.CLE_PARAMS_DT.fields["converge_thres"][1] == 24 and _lib.CLE_PARAMS_DT.fields["max_sweeps"][1] == 36
+    assert _lib.BC_LAYER_DT.fields["flags"][1] == 20 and _lib.BC_LAYER_DT.fields["expect_off"][1] == 24
+    assert _lib.QUANT_TASK_DT.fields["minmax_off"][1] == 24
+
+
+def test_product_refuses_to_run_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dfq_b200 import _lib, dfq
+    with pytest.raises(_lib.DfqError):
+        dfq._layer_equalization(torch.randn(4, 2, 3, 3), torch.randn(4, 4, 3, 3), torch.zeros(4))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under dfq_b200/ or dropin/ may reference it."""
+    for base in ("dfq_b200", "dropin"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(".py"):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)

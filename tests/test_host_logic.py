@@ -1,0 +1,186 @@
+"""Host logic of the drop-in modules, end to end on the CPU: the product's graph walks, arena planning, descriptor
+tables and write-back are executed with `tests/fakelib.py` (the numpy oracle behind the C-ABI signatures) and compared
+with fixtures produced by running the REFERENCE on the same seeded models (tests/golden/ref_*.npz).
+
+What this pins without a GPU: create_relation, merge_batchnorm pairing, relation/step/col_mode planning, the bias
+correction recipe (find_prev_bn, cat/add merging, -delta forwarding, dependency levels), quantize_targ_layer task lists,
+in-place write-back into the module parameters.  The -m gpu suite runs the same checks against the real library."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import fakelib
+from dfq_b200 import workload
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _nw(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def run_pipeline_and_compare(name, seed, gold, tol=1e-5, quantize=True):
+    from dfq_b200 import dfq
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    topo = workload.load_topology(os.path.join(GOLD, "topology_%s.json" % name))
+    graph, bottoms, _ = workload.build_graph(topo, seed=seed)
+    targ = [nn.Conv2d, nn.Linear]
+    keys = list(graph.keys())
+    pos = {k: i for i, k in enumerate(keys)}
+    tl = [k for k in keys if type(graph[k]) in targ]
+    assert np.array_equal(np.array([pos[k] for k in tl]), gold["targets"])
+
+    import hashlib
+    state = {"exact": True}
+
+    def check(tag, tol_w):
+        # Bias correction is ill-conditioned with respect to 1-ulp changes of the weights: a
+        # shifted zero level of the 8-bit grid moves every element's error by the same amount and the mat-vec sums it
+        # over thousands of inputs.  The reference's own sqrt (MKL VML) is not correctly rounded, so downstream of the
+        # equalization the strict 1e-5 check only applies when the equalized weights equal the fixture's bit for bit
+        # (always the case on the machine that produced the fixture); otherwise 5e-2.
+        tol = 1e-5 if (state["exact"] or tag in ("fold", "cle")) else 5e-2
+        for j, k in enumerate(tl):
+            w = graph[k].weight.detach().cpu().numpy()
+            if tag == "cle" and hashlib.sha256(np.ascontiguousarray(w).tobytes()).hexdigest() != str(gold["cle_w_sha"][j]):
+                state["exact"] = False
+            assert abs(np.abs(w).max() - gold[tag + "_w_absmax"][j]) <= tol_w * gold[tag + "_w_absmax"][j], (tag, j)
+            assert abs(w.astype(np.float64).sum() - gold[tag + "_w_sum"][j]) <= 10 * tol_w * np.abs(w).astype(np.float64).sum(), (tag, j)
+            name_b = "%s_bias_%d" % (tag, pos[k])
+            if name_b in gold.files:
+                assert graph[k].bias is not None
+                assert _nw(graph[k].bias.detach().cpu().numpy(), gold[name_b]) < tol, name_b
+        for k in keys:
+            if hasattr(graph[k], "fake_bias") and not isinstance(graph[k], str):
+                assert _nw(graph[k].fake_bias.cpu().numpy(), gold["%s_fb_%d" % (tag, pos[k])]) < tol
+                assert _nw(graph[k].fake_weight.cpu().numpy(), gold["%s_fw_%d" % (tag, pos[k])]) < tol
+
+    LT.merge_batchnorm(None, graph, bottoms, targ)
+    check("fold", 1e-6)
+    rels = create_relation(graph, bottoms, targ)
+    got = np.array([[pos[a], pos[b], pos[c]] for a, b, c in (r.get_idxs() for r in rels)], np.int64)
+    assert np.array_equal(got, gold["relations"])
+    dfq.cross_layer_equalization(graph, rels, targ, converge_thres=2e-7)
+    assert dfq.cross_layer_equalization.last_result.n_sweeps == int(gold["n_sweeps"])
+    for i, r in enumerate(rels):
+        assert _nw(r.S.cpu().numpy(), gold["S_%d" % i]) < tol, "S_%d" % i
+    check("cle", 1e-5)
+    dfq.bias_correction(graph, bottoms, targ)
+    check("bc", 1e-5)
+    if quantize:
+        LT.quantize_targ_layer(graph, 8, 16, targ)
+        check("q", 2e-2)      # a 1-ulp difference before quantization may move a value by one 8-bit step
+    return graph, bottoms, rels
+
+
+def test_resnet18_pipeline_matches_reference_fixture(monkeypatch):
+    fake = fakelib.install(monkeypatch, fakelib.torch_sqrt)
+    gold = np.load(os.path.join(GOLD, "ref_resnet18.npz"))
+    run_pipeline_and_compare("resnet18", 3, gold)
+    assert fake.calls == ["dfq_bn_fold", "dfq_cle_run", "dfq_bias_correct", "dfq_quantize_tensors"]
+
+
+@pytest.mark.timeout(900)
+def test_mobilenetv2_pipeline_matches_reference_fixture(monkeypatch):
+    fakelib.install(monkeypatch, fakelib.torch_sqrt)
+    gold = np.load(os.path.join(GOLD, "ref_mobilenetv2.npz"))
+    graph, bottoms, rels = run_pipeline_and_compare("mobilenetv2", 0, gold)
+    assert len(rels) == 37
+
+
+def test_relation_chains_and_delete_single():
+    from dfq_b200.utils.relation import create_relation
+    for name, n_rel, n_rel_ds in (("mobilenetv2", 37, None), ("resnet18", 8, 0), ("deeplab", 35, None), ("ssd", None, 42)):
+        topo = workload.load_topology(os.path.join(GOLD, "topology_%s.json" % name))
+        graph, bottoms, _ = workload.build_graph(topo, seed=1)
+        targ = [nn.Conv2d, nn.Linear]
+        rels = create_relation(graph, bottoms, targ)
+        if n_rel is not None:
+            assert len(rels) == n_rel, (name, len(rels))
+        if n_rel_ds is not None:
+            assert len(create_relation(graph, bottoms, targ, delete_single=True)) == n_rel_ds, name
+        # forward chain order: the relation whose second is X precedes the relation whose first is X
+        first_at = {r.get_idxs()[0]: i for i, r in enumerate(rels)}
+        for i, r in enumerate(rels):
+            if r.get_idxs()[1] in first_at:
+                assert first_at[r.get_idxs()[1]] > i
+
+
+def test_layer_equalization_entry_point_in_place(monkeypatch):
+    fakelib.install(monkeypatch)
+    from dfq_b200 import dfq
+    from oracle import dfq_oracle as O
+    torch.manual_seed(0)
+    w1, w2, b1 = torch.randn(32, 16, 3, 3), torch.randn(24, 32, 3, 3), torch.randn(32)
+    bw, bb = torch.rand(32) + 0.5, torch.randn(32)
+    n = [t.clone().numpy() for t in (w1, w2, b1, bw, bb)]
+    S_ref = O.layer_equalization(*n, signed=True)
+    p1 = w1.data_ptr()
+    r = dfq._layer_equalization(w1, w2, b1, bw, bb, signed=True)
+    assert r[0] is w1 and r[1] is w2 and r[2] is b1 and w1.data_ptr() == p1
+    for got, want in zip((w1, w2, b1, bw, bb, r[3]), n + [S_ref]):
+        assert np.array_equal(got.numpy(), want)
+
+
+def test_cross_layer_equalization_creates_bias_only_for_first_layers(monkeypatch):
+    fakelib.install(monkeypatch)
+    from dfq_b200 import dfq
+    from dfq_b200.utils.relation import Relation
+    c1, c2 = nn.Conv2d(4, 8, 3, bias=False), nn.Conv2d(8, 6, 3, bias=False)
+    bn = nn.BatchNorm2d(8)
+    bn.register_buffer("fake_weight", torch.rand(8) + 0.5); bn.register_buffer("fake_bias", torch.randn(8))
+    graph = {1: c1, 2: bn, 3: c2}
+    w1_param = c1.weight
+    dfq.cross_layer_equalization(graph, [Relation(1, 3, 2)], [nn.Conv2d])
+    assert c1.bias is not None and c1.bias.requires_grad is False and c2.bias is None   # dfq.py:91-92
+    assert c1.weight is w1_param
+
+
+def test_bias_absorption_and_clip(monkeypatch):
+    fakelib.install(monkeypatch)
+    from dfq_b200 import dfq
+    from dfq_b200.utils.relation import Relation
+    from oracle import dfq_oracle as O
+    torch.manual_seed(2)
+    c1, relu, c2 = nn.Conv2d(4, 8, 3, bias=True), nn.ReLU(), nn.Conv2d(8, 6, 3, bias=False)
+    bn = nn.BatchNorm2d(8)
+    bn.register_buffer("fake_weight", torch.rand(8) * 0.2); bn.register_buffer("fake_bias", torch.randn(8) + 0.5)
+    graph = {1: c1, 2: bn, 3: relu, 4: c2}
+    bottoms = {1: ["Data"], 2: [1], 3: [2], 4: [3]}
+    c = O.bias_absorb_c(bn.fake_weight.numpy(), bn.fake_bias.numpy(), 3)
+    wc = O.bias_absorb_wc(c2.weight.detach().numpy(), c, 8)
+    b1 = c1.bias.detach().numpy().copy(); fb = bn.fake_bias.numpy().copy()
+    dfq.bias_absorption(graph, [Relation(1, 4, 2)], bottoms, 3)
+    assert np.allclose(c1.bias.detach().numpy(), b1 - c) and np.allclose(bn.fake_bias.numpy(), fb - c)
+    assert np.allclose(c2.bias.detach().numpy(), wc, rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        c2.weight.mul_(100)
+    dfq.clip_weight(graph, range_clip=[-15, 15], targ_type=[nn.Conv2d])
+    assert float(c2.weight.max()) <= 15 and float(c2.weight.min()) >= -15
+
+
+def test_quantize_function_and_observer_follow_reference_fixture(monkeypatch):
+    fakelib.install(monkeypatch)
+    from dfq_b200.utils import quantize as Q
+    ops = np.load(os.path.join(GOLD, "ref_ops.npz"))
+    for bits in (8, 4, 16):
+        for sym in (0, 1):
+            x = torch.from_numpy(ops["q_%d_%d_in" % (bits, sym)].copy())
+            y = Q.quantize(x, bits, float(x.min()), float(x.max()), symmetric=bool(sym))
+            assert np.array_equal(y.numpy(), ops["q_%d_%d_out" % (bits, sym)])
+    b = torch.from_numpy(ops["qimp_in"].copy())
+    assert np.array_equal(Q.quantize(b, num_bits=16).numpy(), ops["qimp_out16"])
+    assert np.array_equal(Q.quantize(b, num_bits=8).numpy(), ops["qimp_out8"])
+    # in-place flavour
+    x = torch.from_numpy(ops["q_8_0_in"].copy())
+    y = Q.quantize(x, 8, float(x.min()), float(x.max()), inplace=True)
+    assert np.array_equal(x.numpy(), ops["q_8_0_out"])
+    # set_layer_bits quirk Q1: the activation bit width lands in update_stat, num_bits stays 8
+    conv = Q.QuantNConv2d(3, 4, 3)
+    Q.set_layer_bits({1: conv}, 6, 6, 16, [Q.QuantNConv2d])
+    assert conv.quant.update_stat == 6 and conv.quant.num_bits == 8
