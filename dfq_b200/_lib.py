@@ -25,7 +25,7 @@ class DfqError(RuntimeError):
 LAYER_DT = np.dtype([
     ("w_off", np.int64), ("bias_off", np.int64),
     ("rows", np.int32), ("cols", np.int32), ("kk", np.int32),
-    ("rel_in", np.int32), ("rel_out", np.int32), ("col_mode", np.int32),
+    ("rel_in", np.int32), ("rel_out", np.int32), ("col_mode", np.int32), ("group", np.int32), ("_pad", np.int32),
     ("cmin_off", np.int64), ("cmax_off", np.int64),
 ], align=True)
 
@@ -40,6 +40,7 @@ CLE_PARAMS_DT = np.dtype([
     ("s_lo", np.float32), ("s_hi", np.float32), ("inv_lo", np.float32), ("inv_hi", np.float32),
     ("eps", np.float32), ("signed_mode", np.int32),
     ("converge_thres", np.float64), ("converge_count", np.int32), ("max_sweeps", np.int32),
+    ("apply_only", np.int32), ("_pad", np.int32),
 ], align=True)
 
 CLE_RESULT_DT = np.dtype([
@@ -71,7 +72,7 @@ QUANT_TASK_DT = np.dtype([
 
 # sizes the C side uses (checked in tests against sizeof via the header's layout rules)
 EXPECTED_SIZES = {
-    "DfqLayer": (LAYER_DT, 56), "DfqRelation": (RELATION_DT, 64), "DfqCleParams": (CLE_PARAMS_DT, 40),
+    "DfqLayer": (LAYER_DT, 64), "DfqRelation": (RELATION_DT, 64), "DfqCleParams": (CLE_PARAMS_DT, 48),
     "DfqCleResult": (CLE_RESULT_DT, 528), "DfqFold": (FOLD_DT, 56), "DfqExpectTerm": (TERM_DT, 32),
     "DfqBcLayer": (BC_LAYER_DT, 56), "DfqQuantTask": (QUANT_TASK_DT, 32),
 }
@@ -87,7 +88,7 @@ SIGNATURES = {
     "dfq_struct_size": [C.c_int],
     "dfq_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "dfq_cle_run": [_PF, _I64, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, C.c_void_p, _I32,
-                    C.c_void_p, C.c_void_p, _ST],
+                    C.c_void_p, C.c_void_p, _I32, C.c_void_p, _ST],
     "dfq_bn_fold": [_PF, _I64, C.c_void_p, _I32, C.c_void_p, _I32, _ST],
     "dfq_bias_correct": [_PF, _I64, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, _I32, _I32, _ST],
     "dfq_quantize_tensors": [_PF, _I64, C.c_void_p, _I32, C.c_int, _ST],

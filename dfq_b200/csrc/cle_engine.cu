@@ -36,14 +36,20 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kScanRows = 32;      // rows per column-scan tile
 constexpr int kScanCols = 2048;    // columns kept in shared memory by a scan tile
 
-struct CleCtl {
+// Convergence state of one GROUP of chains.  The reference's exit rule (dfq.py:81-115) is evaluated per model: one
+// group.  A batch of independent models (the synthetic stack: every block is its own model) is calibrated in one
+// launch with one group per model, each stopping on its own.
+struct GroupState {
   double acc[3];   // rotating per-sweep accumulators of sum_l mean|dW_l|
   double diff;     // `diff` of dfq.py:81
   int count;       // `count` of dfq.py:82
   int n_sweeps;
   int done;
   int converged;
-  double diffs[64];
+};
+struct CleCtl {
+  int active[2];   // groups still iterating, double-buffered by sweep parity
+  double diffs[64];  // diff_tmp per sweep of group 0
 };
 
 enum RowKind { RK_W4_1 = 0, RK_W4_4, RK_W4_8, RK_C4_8, RK_WS_1, RK_WS_8, RK_GENERIC };
@@ -138,11 +144,17 @@ __device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCle
   const float cmn = __ldcg(c.cmin_rd + o), cmx = __ldcg(c.cmax_rd + o);
   const float r2 = range_of(cmn, cmx, P.signed_mode);
   float inv;
-  const float s = solve_scale(r1, r2, P, &inv);
+  float s;
+  if (P.apply_only) {          // replay a given scale vector (multi-GPU replicas): s = S[o], columns get 1/S[o]
+    s = __ldcg(c.s_acc + o);
+    inv = __frcp_rn(s);
+  } else {
+    s = solve_scale(r1, r2, P, &inv);
+  }
   if (leader) {
     c.s_step[o] = s;
     __stcg(c.inv_out + o, inv);
-    c.s_acc[o] = c.first_sweep ? s : __fmul_rn(c.s_acc[o], s);
+    if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(c.s_acc[o], s);
     c.bias[o] = __fmul_rn(c.bias[o], s);
     if (c.bnw) c.bnw[o] = __fmul_rn(c.bnw[o], s);
     if (c.bnb) c.bnb[o] = __fmul_rn(c.bnb[o], s);
@@ -356,23 +368,20 @@ __device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int
   }
 }
 
+// scan tiles [t0, t1) of layer li (tile = 32 rows of one group)
 __device__ __forceinline__ void scan_layer(float* arena, const DfqLayer* L, const DfqRelation* R, int li,
-                                           int buf, int& tile_base, float* smin, float* smax) {
+                                           int buf, long long t0, long long t1, float* smin, float* smax) {
   const DfqLayer l = L[li];
   const DfqRelation r = R[l.rel_in];
   const int nb = (r.go + kScanRows - 1) / kScanRows;
-  const int nt = r.groups * nb;
-  int first = (int)(((long long)blockIdx.x - tile_base) % (long long)gridDim.x);
-  if (first < 0) first += gridDim.x;
-  for (int t = first; t < nt; t += gridDim.x) {
-    const int g = t / nb, b = t - g * nb;
+  for (long long t = t0; t < t1; ++t) {
+    const int g = (int)(t / nb), b = (int)(t - (long long)g * nb);
     const int r0 = g * r.go + b * kScanRows;
     const int r1 = min(r0 + kScanRows, (g + 1) * r.go);
     scan_cols_tile(arena + l.w_off, l.cols, l.kk, g, r.gi, r0, r1,
                    arena + l.cmin_off + (size_t)buf * r.channels,
                    arena + l.cmax_off + (size_t)buf * r.channels, smin, smax);
   }
-  tile_base += nt;
 }
 
 __device__ __forceinline__ void reset_cols(float* arena, const DfqLayer& l, const DfqRelation& r, int buf) {
@@ -384,7 +393,9 @@ __device__ __forceinline__ void reset_cols(float* arena, const DfqLayer& l, cons
 __global__ void __launch_bounds__(kThreads, 2)
 k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelation* __restrict__ R, int nR,
              const int* __restrict__ step_ptr, const int* __restrict__ step_layers, int n_steps,
-             const int* __restrict__ step_rescan, DfqCleParams P, CleCtl* ctl) {
+             const int* __restrict__ step_rescan, const long long* __restrict__ pass_ptr,
+             const long long* __restrict__ scan_ptr, const int* __restrict__ scan_layers, int n_scan,
+             DfqCleParams P, CleCtl* ctl, GroupState* G, int nG) {
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[2 * 2 * kWarps];
   __shared__ float smin[kScanCols];
@@ -395,39 +406,57 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- phase 0: column extrema of every `second` layer (buffer 0) -----------------------------
+  for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) G[g].diff = 10.0;   // dfq.py:81
   for (int li = blockIdx.x; li < nL; li += gridDim.x)
     if (L[li].rel_in >= 0) reset_cols(arena, L[li], R[L[li].rel_in], 0);
   grid.sync();
-  {
-    int base = 0;
-    for (int li = 0; li < nL; ++li)
-      if (L[li].rel_in >= 0) scan_layer(arena, L, R, li, 0, base, smin, smax);
+  {  // scan_ptr[0 .. n_scan]: tile prefix over scan_layers (all `second` layers)
+    const TileSpan sp = tile_span(scan_ptr, 0, n_scan);
+    for (int q = sp.q; q < n_scan && scan_ptr[q] < sp.hi; ++q) {
+      const long long base = scan_ptr[q];
+      scan_layer(arena, L, R, scan_layers[q], 0, max(sp.lo, base) - base, min(sp.hi, scan_ptr[q + 1]) - base, smin, smax);
+    }
   }
   grid.sync();
-
-  // exit-rule state, replicated in every CTA's thread 0 (all see the same accumulators)
-  double diff = 10.0;
-  int count = 0;
 
   for (int sweep = 0;; ++sweep) {
     const int slot = sweep % 3;
     for (int p = 0; p < n_steps; ++p) {
       double dacc = 0.0;
-      int base = 0;
-      for (int q = step_ptr[p]; q < step_ptr[p + 1]; ++q) {
+      int cur_g = -1;
+      // sum the CTA's partial of group cur_g into that group's accumulator (one atomic)
+      auto flush = [&]() {
+        if (cur_g < 0) return;
+        dacc = warp_sum(dacc);
+        __syncthreads();
+        if (lane == 0) dred[warp] = dacc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t = 0.0;
+#pragma unroll
+          for (int i = 0; i < kWarps; ++i) t += dred[i];
+          if (t != 0.0) atomicAdd(&G[cur_g].acc[slot], t);
+        }
+        dacc = 0.0;
+      };
+      const TileSpan sp = tile_span(pass_ptr, step_ptr[p], step_ptr[p + 1]);
+      for (int q = sp.q; q < step_ptr[p + 1] && pass_ptr[q] < sp.hi; ++q) {
         const int li = step_layers[q];
+        const long long base = pass_ptr[q];
+        const int t0 = (int)(max(sp.lo, base) - base), t1 = (int)(min(sp.hi, pass_ptr[q + 1]) - base);
+        if (t1 <= t0) continue;
+        const int g = L[li].group;
+        if (*((volatile int*)&G[g].done)) continue;          // this model has converged: its weights are final
+        if (g != cur_g) { flush(); cur_g = g; }
         __syncthreads();                       // previous layer's tiles are done with sctx
         if (threadIdx.x == 0) make_ctx(sctx, arena, L, R, li, sweep);
         __syncthreads();
         const RowCtx& c = sctx;
         const int kind = row_kind(L[li].w_off, c.row_len);
         const int rpt = rows_per_tile(kind);
-        const int nt = (c.rows + rpt - 1) / rpt;
-        int first = (int)(((long long)blockIdx.x - base) % (long long)gridDim.x);
-        if (first < 0) first += gridDim.x;
-        if (L[li].col_mode == 2 && L[li].rel_in >= 0 && first == 0)
+        if (L[li].col_mode == 2 && L[li].rel_in >= 0 && t0 == 0)
           reset_cols(arena, L[li], R[L[li].rel_in], (sweep & 1) ^ 1);
-        for (int t = first; t < nt; t += gridDim.x) {
+        for (int t = t0; t < t1; ++t) {
           if (rpt == 1) {
             if (kind == RK_C4_8) cle_row<8, kThreads, true>(c, P, t, threadIdx.x, red, parity, dacc);
             else cle_row_generic(c, P, t, red, parity, dacc);
@@ -444,43 +473,46 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
             }
           }
         }
-        base += nt;
       }
-      // one atomic per CTA per step
-      dacc = warp_sum(dacc);
-      if (lane == 0) dred[warp] = dacc;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) t += dred[i];
-        if (t != 0.0) atomicAdd(&ctl->acc[slot], t);
-      }
+      flush();
       grid.sync();
-      if (step_rescan[p]) {
-        int sbase = 0;
+      if (step_rescan[p]) {   // general middle layers of this step: round-robin over their scan tiles
+        long long sbase = 0;
         for (int q = step_ptr[p]; q < step_ptr[p + 1]; ++q) {
           const int li = step_layers[q];
-          if (L[li].col_mode == 2 && L[li].rel_in >= 0)
-            scan_layer(arena, L, R, li, (sweep & 1) ^ 1, sbase, smin, smax);
+          if (L[li].col_mode == 2 && L[li].rel_in >= 0 && !*((volatile int*)&G[L[li].group].done)) {
+            const DfqRelation r = R[L[li].rel_in];
+            const long long nt = scan_tiles(r.groups, r.go);
+            long long first = ((long long)blockIdx.x - sbase) % (long long)gridDim.x;
+            if (first < 0) first += gridDim.x;
+            for (long long t = first; t < nt; t += gridDim.x)
+              scan_layer(arena, L, R, li, (sweep & 1) ^ 1, t, t + 1, smin, smax);
+            sbase += nt;
+          }
         }
         grid.sync();
       }
     }
-    // ---- exit rule of dfq.py:105-115, evaluated identically by every CTA -----------------------
-    const double diff_tmp = *((volatile double*)&ctl->acc[slot]);
-    if (fabs(diff - diff_tmp) > 1e-9) { count = 0; diff = diff_tmp; }
-    else count++;
+    // ---- exit rule of dfq.py:105-115, one thread per group ------------------------------------------------
     const int n = sweep + 1;
-    const bool cont = (diff > P.converge_thres) && (count < P.converge_count);
-    const bool stop = !cont || (P.max_sweeps > 0 && n >= P.max_sweeps);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      ctl->acc[(slot + 2) % 3] = 0.0;  // last read before this sweep's final barrier, next used in sweep+2
-      if (sweep < 64) ctl->diffs[sweep] = diff_tmp;
-      if (stop) { ctl->n_sweeps = n; ctl->diff = diff; ctl->count = count; ctl->converged = !cont; ctl->done = 1; }
-      __threadfence();
+    for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) {
+      GroupState& st = G[g];
+      if (st.done) continue;
+      const double diff_tmp = st.acc[slot];
+      st.acc[(slot + 2) % 3] = 0.0;   // last read before this sweep's final barrier, next used in sweep+2
+      if (fabs(st.diff - diff_tmp) > 1e-9) { st.count = 0; st.diff = diff_tmp; }
+      else st.count++;
+      if (g == 0 && sweep < 64) ctl->diffs[sweep] = diff_tmp;
+      const bool cont = (st.diff > P.converge_thres) && (st.count < P.converge_count);
+      // safety net: the reference's loop has no bound; 4096 sweeps is ~80x what any of its models needs
+      const int cap = P.max_sweeps > 0 ? P.max_sweeps : 4096;
+      if (!cont || n >= cap) { st.n_sweeps = n; st.converged = !cont; st.done = 1; }
+      else atomicAdd(&ctl->active[n & 1], 1);
     }
-    if (stop) break;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->active[sweep & 1] = 0;   // read at the end of the previous sweep
+    __threadfence();
+    grid.sync();
+    if (*((volatile int*)&ctl->active[n & 1]) == 0) break;
   }
 }
 
@@ -491,10 +523,10 @@ using namespace dfq;
 extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* layers, int32_t n_layers,
                            const DfqRelation* rels, int32_t n_rels, const int32_t* step_ptr,
                            const int32_t* step_layers, int32_t n_steps, const DfqCleParams* params,
-                           DfqCleResult* result, void* stream) {
+                           DfqCleResult* result, int32_t n_groups, int32_t* group_sweeps, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DFQ_REQUIRE(arena && layers && rels && step_ptr && step_layers && params && result, "null argument");
-  DFQ_REQUIRE(n_layers > 0 && n_rels > 0 && n_steps > 0, "empty problem");
+  DFQ_REQUIRE(n_layers > 0 && n_rels > 0 && n_steps > 0 && n_groups > 0, "empty problem");
   memset(result, 0, sizeof(*result));
   // Python `while diff > thres and count < converge_count` with diff = 10, count = 0 (dfq.py:81-83)
   if (!(10.0 > params->converge_thres) || !(0 < params->converge_count)) { result->converged = 1; result->last_diff = 10.0; return 0; }
@@ -511,6 +543,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     DFQ_REQUIRE(r.groups >= 1 && r.groups * r.gi == r.channels && r.groups * r.go == b.rows, "relation grouping");
     DFQ_REQUIRE(r.gi == b.cols, "first.rows / groups must equal second.cols (dfq.py:29-35)");
     DFQ_REQUIRE(a.rel_out == i && b.rel_in == i, "layer/relation cross links");
+    DFQ_REQUIRE(a.group == b.group, "both layers of a relation must belong to the same convergence group");
     DFQ_REQUIRE(r.s_acc_off >= 0 && r.s_step_off >= 0 && r.inv_off >= 0, "relation scratch offsets");
     DFQ_REQUIRE(b.cmin_off >= 0 && b.cmax_off >= 0, "second layer needs column range scratch");
     DFQ_REQUIRE(b.col_mode != 1 || (b.cols == 1 && r.go == 1), "col_mode 1 requires cols==1 and one row per group");
@@ -519,6 +552,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   for (int i = 0; i < n_layers; ++i) {
     const DfqLayer& l = layers[i];
     DFQ_REQUIRE(l.rows > 0 && l.cols > 0 && l.kk > 0, "layer shape");
+    DFQ_REQUIRE(l.group >= 0 && l.group < n_groups, "layer group index");
     DFQ_REQUIRE(l.w_off >= 0 && l.w_off + (int64_t)l.rows * l.cols * l.kk <= arena_floats, "weight outside arena");
     DFQ_REQUIRE(l.bias_off >= 0 && l.bias_off + l.rows <= arena_floats, "bias outside arena");
     if (l.rel_in >= 0 && l.rel_out >= 0) DFQ_REQUIRE(l.rel_in < l.rel_out, "relations must be in forward chain order");
@@ -549,28 +583,55 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   if (per_sm < 1) { set_error("persistent kernel does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
   const int grid = (int)std::min<int64_t>((int64_t)sms * per_sm, max_tiles);
 
+  const int n_entries = step_ptr[n_steps];
+  std::vector<long long> pass_ptr(n_entries + 1, 0);
+  for (int q = 0; q < n_entries; ++q) pass_ptr[q + 1] = pass_ptr[q] + pass_tiles(layers[step_layers[q]]);
+  std::vector<int32_t> scan_layers;
+  std::vector<long long> scan_ptr(1, 0);
+  for (int i = 0; i < n_layers; ++i)
+    if (layers[i].rel_in >= 0) {
+      scan_layers.push_back(i);
+      scan_ptr.push_back(scan_ptr.back() + scan_tiles(rels[layers[i].rel_in].groups, rels[layers[i].rel_in].go));
+    }
+  int n_scan = (int)scan_layers.size();
+  long long *dPP = nullptr, *dSCP = nullptr; int32_t* dSCL = nullptr;
   DfqLayer* dL = nullptr; DfqRelation* dR = nullptr; int32_t *dSP = nullptr, *dSL = nullptr, *dRS = nullptr;
   CleCtl* dctl = nullptr;
+  GroupState* dG = nullptr;
   int rc;
   if ((rc = upload(layers, n_layers, &dL, st))) return rc;
   if ((rc = upload(rels, n_rels, &dR, st))) return rc;
   if ((rc = upload(step_ptr, n_steps + 1, &dSP, st))) return rc;
   if ((rc = upload(step_layers, step_ptr[n_steps], &dSL, st))) return rc;
   if ((rc = upload(rescan.data(), n_steps, &dRS, st))) return rc;
+  if ((rc = upload(pass_ptr.data(), n_entries + 1, &dPP, st))) return rc;
+  if ((rc = upload(scan_ptr.data(), n_scan + 1, &dSCP, st))) return rc;
+  if ((rc = upload(scan_layers.data(), n_scan, &dSCL, st))) return rc;
   DFQ_CUDA(cudaMallocAsync((void**)&dctl, sizeof(CleCtl), st));
   DFQ_CUDA(cudaMemsetAsync(dctl, 0, sizeof(CleCtl), st));
+  DFQ_CUDA(cudaMallocAsync((void**)&dG, sizeof(GroupState) * n_groups, st));
+  DFQ_CUDA(cudaMemsetAsync(dG, 0, sizeof(GroupState) * n_groups, st));
 
   DfqCleParams P = *params;
-  void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS, &P, &dctl};
+  void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS,
+                  &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kThreads), args, 0, st));
   CleCtl h;
+  std::vector<GroupState> hg(n_groups);
   DFQ_CUDA(cudaMemcpyAsync(&h, dctl, sizeof(CleCtl), cudaMemcpyDeviceToHost, st));
+  DFQ_CUDA(cudaMemcpyAsync(hg.data(), dG, sizeof(GroupState) * n_groups, cudaMemcpyDeviceToHost, st));
   free_async(dL, st); free_async(dR, st); free_async(dSP, st); free_async(dSL, st); free_async(dRS, st);
-  free_async(dctl, st);
+  free_async(dPP, st); free_async(dSCP, st); free_async(dSCL, st);
+  free_async(dctl, st); free_async(dG, st);
   DFQ_CUDA(cudaStreamSynchronize(st));
-  result->n_sweeps = h.n_sweeps;
-  result->converged = h.converged;
-  result->last_diff = h.diff;
+  result->n_sweeps = 0;
+  result->converged = 1;
+  for (int g = 0; g < n_groups; ++g) {
+    result->n_sweeps = std::max(result->n_sweeps, hg[g].n_sweeps);
+    result->converged &= hg[g].converged;
+    if (group_sweeps) group_sweeps[g] = hg[g].n_sweeps;
+  }
+  result->last_diff = hg[0].diff;
   memcpy(result->diffs, h.diffs, sizeof(h.diffs));
   return 0;
 }

@@ -97,6 +97,29 @@ __device__ __forceinline__ void atomic_max_f(float* addr, float v) {
   else          atomicMin((unsigned int*)addr, __float_as_uint(v));
 }
 
+// ------------------------------------------------------------------------------------------
+// blocked tile partition: the tiles of a phase are numbered consecutively over its task list
+// (ptr[q] = first tile of task q, ptr[n] = total); CTA b owns the contiguous range
+// [b*T/G, (b+1)*T/G).  A CTA therefore touches only the few tasks its range intersects.
+// ------------------------------------------------------------------------------------------
+struct TileSpan {
+  long long lo, hi;   // global tile range of this CTA
+  int q;              // first task intersecting it
+};
+__device__ __forceinline__ TileSpan tile_span(const long long* __restrict__ ptr, int q_begin, int q_end) {
+  TileSpan s;
+  const long long first = ptr[q_begin], total = ptr[q_end] - first;
+  s.lo = first + (long long)blockIdx.x * total / gridDim.x;
+  s.hi = first + (long long)(blockIdx.x + 1) * total / gridDim.x;
+  int a = q_begin, b = q_end;   // largest q in [q_begin, q_end) with ptr[q] <= lo
+  while (b - a > 1) {
+    const int m = (a + b) >> 1;
+    if (ptr[m] <= s.lo) a = m; else b = m;
+  }
+  s.q = a;
+  return s;
+}
+
 __device__ __forceinline__ float ld_volatile_f(const float* p) {
   return *(const volatile float*)p;
 }

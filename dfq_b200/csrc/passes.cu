@@ -30,18 +30,20 @@ __device__ __forceinline__ int first_tile(long long base) {
 // BN fold
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restrict__ F, int nF) {
+k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restrict__ F, int nF,
+          const long long* __restrict__ tptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long base = 0;
-  for (int fi = 0; fi < nF; ++fi) {
+  const TileSpan sp = tile_span(tptr, 0, nF);
+  for (int fi = sp.q; fi < nF && tptr[fi] < sp.hi; ++fi) {
+    const long long base = tptr[fi];
     const DfqFold f = F[fi];
     const DfqLayer l = L[f.layer];
     const int row_len = l.cols * l.kk;
     const bool vec = (row_len % 4 == 0) && (l.w_off % 4 == 0);
     const bool cta_row = row_len > 2048;
     const int rpt = cta_row ? 1 : kWarps;
-    const int nt = (l.rows + rpt - 1) / rpt;
-    for (int t = first_tile(base); t < nt; t += gridDim.x) {
+    const int t0 = (int)(max(sp.lo, base) - base), t1 = (int)(min(sp.hi, tptr[fi + 1]) - base);
+    for (int t = t0; t < t1; ++t) {
       const int o = cta_row ? t : t * kWarps + warp;
       if (o >= l.rows) continue;
       const int tid = cta_row ? (int)threadIdx.x : lane;
@@ -72,7 +74,6 @@ k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restric
         arena[f.fake_b_off + o] = beta;           // :265
       }
     }
-    base += nt;
   }
 }
 
@@ -127,34 +128,34 @@ __global__ void k_minmax_init(float* arena, const FlatTask* __restrict__ T, int 
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_minmax_tasks(float* arena, const FlatTask* __restrict__ T, int nT) {
+k_minmax_tasks(float* arena, const FlatTask* __restrict__ T, int nT, const long long* __restrict__ tptr) {
   __shared__ float red[2 * kWarps];
-  long long base = 0;
-  for (int ti = 0; ti < nT; ++ti) {
+  const TileSpan sp = tile_span(tptr, 0, nT);
+  for (int ti = sp.q; ti < nT && tptr[ti] < sp.hi; ++ti) {
     const FlatTask t = T[ti];
-    const long long nt = (t.n + kChunk - 1) / kChunk;
+    const long long base = tptr[ti];
+    const long long k0 = max(sp.lo, base) - base, k1 = min(sp.hi, tptr[ti + 1]) - base;
+    if (k1 <= k0) continue;
     float mn = DFQ_INF, mx = -DFQ_INF;
-    bool any = false;
-    for (long long k = first_tile(base); k < nt; k += gridDim.x) { tile_minmax(arena + t.off, t.n, k, mn, mx); any = true; }
-    if (any) cta_minmax_atomic(mn, mx, arena + t.minmax_off, red);   // `any` is CTA-uniform
-    base += nt;
+    for (long long k = k0; k < k1; ++k) tile_minmax(arena + t.off, t.n, k, mn, mx);
+    cta_minmax_atomic(mn, mx, arena + t.minmax_off, red);
   }
 }
 
 template <bool RECIP>
 __global__ void __launch_bounds__(kThreads)
-k_quant_tasks(float* arena, const FlatTask* __restrict__ T, int nT) {
-  long long base = 0;
-  for (int ti = 0; ti < nT; ++ti) {
+k_quant_tasks(float* arena, const FlatTask* __restrict__ T, int nT, const long long* __restrict__ tptr) {
+  const TileSpan sp = tile_span(tptr, 0, nT);
+  for (int ti = sp.q; ti < nT && tptr[ti] < sp.hi; ++ti) {
     const FlatTask t = T[ti];
-    const long long nt = (t.n + kChunk - 1) / kChunk;
-    const int f = first_tile(base);
-    if (f < nt) {
+    const long long base = tptr[ti];
+    const long long k0 = max(sp.lo, base) - base, k1 = min(sp.hi, tptr[ti + 1]) - base;
+    if (k1 > k0) {
       // float(param.min()), float(param.max()) -> Python doubles (layer_transform.py:289,294)
       const QuantScalars q = quant_scalars((double)__ldcg(arena + t.minmax_off), (double)__ldcg(arena + t.minmax_off + 1),
                                            t.num_bits, t.symmetric);
       float* x = arena + t.off;
-      for (long long k = f; k < nt; k += gridDim.x) {
+      for (long long k = k0; k < k1; ++k) {
         const int64_t lo = k * kChunk, hi = min(lo + (int64_t)kChunk, t.n);
         if ((t.off & 3) == 0) {
           float4* x4 = (float4*)x;
@@ -171,7 +172,6 @@ k_quant_tasks(float* arena, const FlatTask* __restrict__ T, int nT) {
         }
       }
     }
-    base += nt;
   }
 }
 
@@ -203,7 +203,8 @@ __device__ __forceinline__ float relu_gauss_mean(float g, float b) {
 
 __global__ void __launch_bounds__(kThreads, 2)
 k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __restrict__ B, int nB,
-            const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits) {
+            const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits,
+            const long long* __restrict__ mm_ptr, const long long* __restrict__ row_ptr) {
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[2 * kWarps];
   __shared__ double dred[kWarps];
@@ -216,16 +217,16 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
   }
   grid.sync();
   {
-    long long base = 0;
-    for (int bi = 0; bi < nB; ++bi) {
+    const TileSpan sp = tile_span(mm_ptr, 0, nB);
+    for (int bi = sp.q; bi < nB && mm_ptr[bi] < sp.hi; ++bi) {
+      const long long base = mm_ptr[bi];
+      const long long k0 = max(sp.lo, base) - base, k1 = min(sp.hi, mm_ptr[bi + 1]) - base;
+      if (k1 <= k0) continue;
       const DfqLayer l = L[B[bi].layer];
       const int64_t n = (int64_t)l.rows * l.cols * l.kk;
-      const long long nt = (n + kChunk - 1) / kChunk;
       float mn = DFQ_INF, mx = -DFQ_INF;
-      bool any = false;
-      for (long long k = first_tile(base); k < nt; k += gridDim.x) { tile_minmax(arena + l.w_off, n, k, mn, mx); any = true; }
-      if (any) cta_minmax_atomic(mn, mx, arena + B[bi].minmax_off, red);
-      base += nt;
+      for (long long k = k0; k < k1; ++k) tile_minmax(arena + l.w_off, n, k, mn, mx);
+      cta_minmax_atomic(mn, mx, arena + B[bi].minmax_off, red);
     }
   }
   grid.sync();
@@ -248,21 +249,20 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
     }
     grid.sync();
     // ---- eps . E[x] per output row (dfq.py:216-219,281-293) ------------------------------------------
-    long long base = 0;
-    for (int bi = level_ptr[lev]; bi < level_ptr[lev + 1]; ++bi) {
+    const TileSpan sp = tile_span(row_ptr, level_ptr[lev], level_ptr[lev + 1]);
+    for (int bi = sp.q; bi < level_ptr[lev + 1] && row_ptr[bi] < sp.hi; ++bi) {
+      const long long base = row_ptr[bi];
+      const int t0 = (int)(max(sp.lo, base) - base), t1 = (int)(min(sp.hi, row_ptr[bi + 1]) - base);
       const DfqBcLayer b = B[bi];
       const DfqLayer l = L[b.layer];
       const int row_len = l.cols * l.kk;
       const bool cta_row = row_len > 2048;
-      const int rpt = cta_row ? 1 : kWarps;
-      const int nt = (l.rows + rpt - 1) / rpt;
-      const int f = first_tile(base);
-      if (f < nt) {
+      if (t1 > t0) {
         const QuantScalars q = quant_scalars((double)__ldcg(arena + b.minmax_off), (double)__ldcg(arena + b.minmax_off + 1),
                                              num_bits, b.signed_mode);
         const int G = b.expect_len / l.cols;
         const int so = l.rows / G;
-        for (int t = f; t < nt; t += gridDim.x) {
+        for (int t = t0; t < t1; ++t) {
           const int o = cta_row ? t : t * kWarps + warp;
           const bool live = o < l.rows;
           double acc = 0.0;
@@ -304,7 +304,6 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
           }
         }
       }
-      base += nt;
     }
     grid.sync();
   }
@@ -329,21 +328,22 @@ extern "C" int dfq_bn_fold(float* arena, int64_t arena_floats, const DfqLayer* l
   cudaStream_t st = (cudaStream_t)stream;
   DFQ_REQUIRE(arena && layers && folds, "null argument");
   if (n_folds <= 0) return 0;
-  int64_t tiles = 0;
+  std::vector<long long> tptr(n_folds + 1, 0);
   for (int i = 0; i < n_folds; ++i) {
     DFQ_REQUIRE(folds[i].layer >= 0 && folds[i].layer < n_layers, "fold layer index");
     const DfqLayer& l = layers[folds[i].layer];
     DFQ_REQUIRE(l.w_off >= 0 && l.w_off + (int64_t)l.rows * l.cols * l.kk <= arena_floats, "weight outside arena");
-    tiles += (l.cols * l.kk > 2048) ? l.rows : (l.rows + kWarps - 1) / kWarps;
+    tptr[i + 1] = tptr[i] + ((l.cols * l.kk > 2048) ? l.rows : (l.rows + kWarps - 1) / kWarps);
   }
   int grid, rc;
-  if ((rc = pick_grid((const void*)k_bn_fold, tiles, &grid))) return rc;
-  DfqLayer* dL; DfqFold* dF;
+  if ((rc = pick_grid((const void*)k_bn_fold, tptr[n_folds], &grid))) return rc;
+  DfqLayer* dL; DfqFold* dF; long long* dP;
   if ((rc = upload(layers, n_layers, &dL, st))) return rc;
   if ((rc = upload(folds, n_folds, &dF, st))) return rc;
-  k_bn_fold<<<grid, kThreads, 0, st>>>(arena, dL, dF, n_folds);
+  if ((rc = upload(tptr.data(), n_folds + 1, &dP, st))) return rc;
+  k_bn_fold<<<grid, kThreads, 0, st>>>(arena, dL, dF, n_folds, dP);
   DFQ_CUDA(cudaGetLastError());
-  free_async(dL, st); free_async(dF, st);
+  free_async(dL, st); free_async(dF, st); free_async(dP, st);
   return 0;
 }
 
@@ -353,24 +353,25 @@ extern "C" int dfq_quantize_tensors(float* arena, int64_t arena_floats, const Df
   DFQ_REQUIRE(arena && tasks, "null argument");
   if (n_tasks <= 0) return 0;
   std::vector<FlatTask> ft(n_tasks);
-  int64_t tiles = 0;
+  std::vector<long long> tptr(n_tasks + 1, 0);
   for (int i = 0; i < n_tasks; ++i) {
     DFQ_REQUIRE(tasks[i].off >= 0 && tasks[i].n > 0 && tasks[i].off + tasks[i].n <= arena_floats, "tensor outside arena");
     DFQ_REQUIRE(tasks[i].minmax_off >= 0 && tasks[i].minmax_off + 2 <= arena_floats, "minmax scratch outside arena");
     DFQ_REQUIRE(tasks[i].num_bits >= 1 && tasks[i].num_bits <= 32, "num_bits");
     ft[i] = {tasks[i].off, tasks[i].n, tasks[i].minmax_off, tasks[i].num_bits, tasks[i].symmetric};
-    tiles += (tasks[i].n + kChunk - 1) / kChunk;
+    tptr[i + 1] = tptr[i] + (tasks[i].n + kChunk - 1) / kChunk;
   }
   int grid, rc;
-  if ((rc = pick_grid((const void*)k_minmax_tasks, tiles, &grid))) return rc;
-  FlatTask* dT;
+  if ((rc = pick_grid((const void*)k_minmax_tasks, tptr[n_tasks], &grid))) return rc;
+  FlatTask* dT; long long* dP;
   if ((rc = upload(ft.data(), n_tasks, &dT, st))) return rc;
+  if ((rc = upload(tptr.data(), n_tasks + 1, &dP, st))) return rc;
   k_minmax_init<<<std::min(148, (n_tasks + 255) / 256), 256, 0, st>>>(arena, dT, n_tasks);
-  k_minmax_tasks<<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
-  if (div_mode) k_quant_tasks<true><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
-  else          k_quant_tasks<false><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks);
+  k_minmax_tasks<<<grid, kThreads, 0, st>>>(arena, dT, n_tasks, dP);
+  if (div_mode) k_quant_tasks<true><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks, dP);
+  else          k_quant_tasks<false><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks, dP);
   DFQ_CUDA(cudaGetLastError());
-  free_async(dT, st);
+  free_async(dT, st); free_async(dP, st);
   return 0;
 }
 
@@ -382,6 +383,7 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   if (n_bc <= 0 || n_levels <= 0) return 0;
   DFQ_REQUIRE(level_ptr[0] == 0 && level_ptr[n_levels] == n_bc, "levels must partition the layer list");
   int64_t max_tiles = 1, mm_tiles = 0;
+  std::vector<long long> mm_ptr(n_bc + 1, 0), row_ptr(n_bc + 1, 0);
   for (int i = 0; i < n_bc; ++i) {
     const DfqBcLayer& b = bc[i];
     DFQ_REQUIRE(b.layer >= 0 && b.layer < n_layers, "bc layer index");
@@ -393,6 +395,8 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
       DFQ_REQUIRE(terms[t].dst_off >= 0 && terms[t].dst_off + terms[t].n <= b.expect_len, "term outside expectation vector");
     DFQ_REQUIRE(b.expect_off >= 0 && b.expect_off + b.expect_len <= arena_floats, "expect scratch outside arena");
     mm_tiles += ((int64_t)l.rows * l.cols * l.kk + kChunk - 1) / kChunk;
+    mm_ptr[i + 1] = mm_tiles;
+    row_ptr[i + 1] = row_ptr[i] + ((l.cols * l.kk > 2048) ? l.rows : (l.rows + kWarps - 1) / kWarps);
   }
   max_tiles = std::max(max_tiles, mm_tiles);
   for (int lev = 0; lev < n_levels; ++lev) {
@@ -405,13 +409,15 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   }
   int grid, rc;
   if ((rc = pick_grid((const void*)k_bc_engine, max_tiles, &grid))) return rc;
-  DfqLayer* dL; DfqBcLayer* dB; DfqExpectTerm* dT; int32_t* dLP;
+  DfqLayer* dL; DfqBcLayer* dB; DfqExpectTerm* dT; int32_t* dLP; long long *dMP, *dRP;
   if ((rc = upload(layers, n_layers, &dL, st))) return rc;
   if ((rc = upload(bc, n_bc, &dB, st))) return rc;
   if ((rc = upload(terms, n_terms, &dT, st))) return rc;
   if ((rc = upload(level_ptr, n_levels + 1, &dLP, st))) return rc;
-  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits};
+  if ((rc = upload(mm_ptr.data(), n_bc + 1, &dMP, st))) return rc;
+  if ((rc = upload(row_ptr.data(), n_bc + 1, &dRP, st))) return rc;
+  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dMP, &dRP};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, 0, st));
-  free_async(dL, st); free_async(dB, st); free_async(dT, st); free_async(dLP, st);
+  free_async(dL, st); free_async(dB, st); free_async(dT, st); free_async(dLP, st); free_async(dMP, st); free_async(dRP, st);
   return 0;
 }

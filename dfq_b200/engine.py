@@ -34,10 +34,11 @@ def _round_up(x: int, a: int) -> int:
 
 @dataclass
 class CleResult:
-    n_sweeps: int
+    n_sweeps: int            # max over convergence groups
     converged: bool
     last_diff: float
-    diffs: List[float]
+    diffs: List[float]       # diff_tmp per sweep of group 0
+    group_sweeps: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -180,6 +181,7 @@ class Session:
                     b.tensor.detach().copy_(self.arena[b.off: b.off + b.n].reshape(b.tensor.shape))
 
     def view(self, off: int, n: int) -> torch.Tensor:
+        self._ensure_room()
         return self.arena[off: off + n]
 
     # ---- tables ------------------------------------------------------------------------------------
@@ -188,7 +190,7 @@ class Session:
         for i, l in enumerate(self._layers):
             t[i]["w_off"] = l["w_off"]; t[i]["bias_off"] = l["bias_off"]
             t[i]["rows"] = l["rows"]; t[i]["cols"] = l["cols"]; t[i]["kk"] = l["kk"]
-            t[i]["rel_in"] = -1; t[i]["rel_out"] = -1; t[i]["col_mode"] = 0
+            t[i]["rel_in"] = -1; t[i]["rel_out"] = -1; t[i]["col_mode"] = 0; t[i]["group"] = 0
             t[i]["cmin_off"] = -1; t[i]["cmax_off"] = -1
             if roles and i in roles:
                 for k, v in roles[i].items():
@@ -217,10 +219,16 @@ class Session:
                                         _lib.table_ptr(ft), len(ft), _lib.stream_ptr()), "dfq_bn_fold")
 
     # ---- cross-layer equalization -----------------------------------------------------------------
-    def plan_cle(self, relations: Sequence[Tuple[int, int, int, int]]) -> dict:
+    def plan_cle(self, relations: Sequence[Tuple[int, int, int, int]], groups: Optional[Sequence[int]] = None) -> dict:
         """Build the descriptor tables + scratch for a list of relations
-        (first_layer, second_layer, bn_w_off | -1, bn_b_off | -1) in processing order (dfq.py:85-86)."""
+        (first_layer, second_layer, bn_w_off | -1, bn_b_off | -1) in processing order (dfq.py:85-86).
+
+        groups[i] = convergence group (independent model) of relation i; default: one group, i.e. the reference's
+        single-model exit rule.  All relations of a chain must share a group."""
         nR = len(relations)
+        if groups is None:
+            groups = [0] * nR
+        n_groups = max(groups) + 1
         rel_in: Dict[int, int] = {}
         rel_out: Dict[int, int] = {}
         for i, (a, b, _, _) in enumerate(relations):
@@ -247,8 +255,10 @@ class Session:
             r["s_acc_off"] = self.alloc(C1); r["s_step_off"] = self.alloc(C1); r["inv_off"] = self.alloc(C1)
             s_offs.append(int(r["s_acc_off"]))
             roles.setdefault(a, {})["rel_out"] = i
+            roles[a]["group"] = int(groups[i])
             rb = roles.setdefault(b, {})
             rb["rel_in"] = i
+            rb["group"] = int(groups[i])
             rb["cmin_off"] = self.alloc(2 * C1); rb["cmax_off"] = self.alloc(2 * C1)
         for l, ro in roles.items():
             if "rel_in" in ro:
@@ -273,10 +283,10 @@ class Session:
             step_ptr[p + 1] = step_ptr[p] + len(buckets[p])
         step_layers = np.array([l for bk in buckets for l in bk], dtype=np.int32)
         return dict(rt=rt, lt=self._layer_table(roles), step_ptr=step_ptr, step_layers=step_layers, n_steps=n_steps,
-                    s_offs=s_offs, relations=list(relations))
+                    s_offs=s_offs, relations=list(relations), n_groups=n_groups)
 
     def run_cle_plan(self, plan: dict, s_range=(1e-8, 1e8), converge_thres=2e-7, converge_count=20, signed=False,
-                     eps=0, max_sweeps=0) -> CleResult:
+                     eps=0, max_sweeps=0, apply_only=False) -> CleResult:
         """Run dfq.py:78-117 on a planned relation list; see include/dfq_b200.h dfq_cle_run."""
         self._ensure_room()
         lo, hi = float(s_range[0]), float(s_range[1])
@@ -287,15 +297,20 @@ class Session:
             P[0]["inv_hi"] = np.float32(np.float64(1.0) / np.float64(hi)) if hi != 0 else np.float32(np.inf)
         P[0]["eps"] = np.float32(eps); P[0]["signed_mode"] = 1 if signed else 0
         P[0]["converge_thres"] = float(converge_thres); P[0]["converge_count"] = int(converge_count)
-        P[0]["max_sweeps"] = int(max_sweeps)
+        P[0]["max_sweeps"] = 1 if apply_only else int(max_sweeps)
+        P[0]["apply_only"] = 1 if apply_only else 0
         R = np.zeros(1, dtype=_lib.CLE_RESULT_DT)
         lt, rt = plan["lt"], plan["rt"]
+        gs = np.zeros(plan["n_groups"], dtype=np.int32)
         _lib.check(self.lib.dfq_cle_run(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
                                         _lib.table_ptr(rt), len(rt), _lib.table_ptr(plan["step_ptr"]),
                                         _lib.table_ptr(plan["step_layers"]), plan["n_steps"], _lib.table_ptr(P),
-                                        _lib.table_ptr(R), _lib.stream_ptr()), "dfq_cle_run")
+                                        _lib.table_ptr(R), plan["n_groups"], _lib.table_ptr(gs), _lib.stream_ptr()),
+                   "dfq_cle_run")
         n = int(R[0]["n_sweeps"])
-        return CleResult(n, bool(R[0]["converged"]), float(R[0]["last_diff"]), [float(x) for x in R[0]["diffs"][:min(n, 64)]])
+        res = CleResult(n, bool(R[0]["converged"]), float(R[0]["last_diff"]), [float(x) for x in R[0]["diffs"][:min(n, 64)]])
+        res.group_sweeps = gs
+        return res
 
     def run_cle(self, relations: Sequence[Tuple[int, int, int, int]], s_range=(1e-8, 1e8), converge_thres=2e-7,
                 converge_count=20, signed=False, eps=0, max_sweeps=0) -> Tuple[CleResult, List[int]]:

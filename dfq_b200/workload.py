@@ -194,7 +194,8 @@ class DeviceStack:
         self.fold_plan = sess.plan_bn_fold(folds)
         rels = [(self.layers[2 * b], self.layers[2 * b + 1], self.vec[2 * b]["fake_w"], self.vec[2 * b]["fake_b"])
                 for b in range(n_blocks)]
-        self.cle_plan = sess.plan_cle(rels)
+        # every block is an independent model: its own convergence group (the reference would be called per model)
+        self.cle_plan = sess.plan_cle(rels, groups=list(range(n_blocks)))
         items = [dict(layer=self.layers[2 * b + 1], signed=False, level=0, next_bn_b_off=self.vec[2 * b + 1]["fake_b"],
                       terms=[dict(bn_w_off=self.vec[2 * b]["fake_w"], bn_b_off=self.vec[2 * b]["fake_b"], n=C, relu=True, op="set")])
                  for b in range(n_blocks)]

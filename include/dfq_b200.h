@@ -71,6 +71,8 @@ typedef struct DfqLayer {
                          0 = chain end: only column-scaled  -> ranges updated analytically
                          1 = depthwise middle (cols==1, one row per group) -> analytic as well
                          2 = general middle layer -> re-scanned after its pass               */
+  int32_t group;      /* convergence group (= model) this layer belongs to, 0 .. n_groups-1    */
+  int32_t _pad;
   int64_t cmin_off;   /* [2][C of rel_in] running column minima, double-buffered by sweep parity
                          (scratch, valid when rel_in >= 0)                                  */
   int64_t cmax_off;   /* [2][C of rel_in] running column maxima                              */
@@ -100,6 +102,9 @@ typedef struct DfqCleParams {
   double converge_thres;   /* dfq.py:78 */
   int32_t converge_count;
   int32_t max_sweeps;      /* >0: stop after this many sweeps regardless (1 = one _layer_equalization pass) */
+  int32_t apply_only;      /* 1: do not solve - take s from s_acc (a scale vector computed elsewhere) and apply it:
+                              rows of `first` *= S, columns of `second` *= 1/S.  Use with max_sweeps = 1. */
+  int32_t _pad;
 } DfqCleParams;
 
 typedef struct DfqCleResult {
@@ -118,12 +123,21 @@ typedef struct DfqCleResult {
  * utils/relation.py:61-68 produces.  One persistent cooperative kernel runs all sweeps; the exit
  * rule of dfq.py:105-115 is evaluated on the device; the convergence metric sums mean|W - W_prev|
  * over the layers listed in the steps (layers outside every relation never change, so their term of
- * dfq.py:105-108 is zero).  Synchronises (result is read back). */
+ * dfq.py:105-108 is zero).  Synchronises (result is read back).
+ *
+ * Convergence groups.  The reference calibrates ONE model per call, and its exit rule sums over that model's
+ * layers.  A batch of independent models (e.g. the synthetic stack of BASELINE.json, whose blocks are independent
+ * two-layer models) is passed as n_groups > 1 with DfqLayer.group naming the model of each layer: every group is
+ * iterated until ITS exit rule fires - exactly what one reference call per model would do - while all groups
+ * share the launch.  result->n_sweeps is the maximum over groups, ->converged the conjunction, ->diffs and
+ * ->last_diff belong to group 0. */
 int dfq_cle_run(float* arena, int64_t arena_floats,
                 const DfqLayer* layers, int32_t n_layers,
                 const DfqRelation* rels, int32_t n_rels,
                 const int32_t* step_ptr, const int32_t* step_layers, int32_t n_steps,
-                const DfqCleParams* params, DfqCleResult* result, void* stream);
+                const DfqCleParams* params, DfqCleResult* result,
+                int32_t n_groups, int32_t* group_sweeps /* host, [n_groups] sweeps run per group, or NULL */,
+                void* stream);
 
 /* BN fold (utils/layer_transform.py:231-276, merge_batchnorm), batched over layers.
  * W[o,:] *= gamma[o]/sqrt(var[o]+eps); b = b*f + (beta - gamma*mean/sqrt(var+eps));

@@ -53,7 +53,7 @@ class FakeLib:
         n = int(l["rows"]) * int(l["cols"]) * int(l["kk"])
         return arena[int(l["w_off"]): int(l["w_off"]) + n].reshape(int(l["rows"]), int(l["cols"]), int(l["kk"]))
 
-    def dfq_cle_run(self, arena_p, n_arena, lt_p, nL, rt_p, nR, sp_p, sl_p, n_steps, P_p, R_p, stream):
+    def dfq_cle_run(self, arena_p, n_arena, lt_p, nL, rt_p, nR, sp_p, sl_p, n_steps, P_p, R_p, n_groups, gs_p, stream):
         self.calls.append("dfq_cle_run")
         arena = _floats(arena_p, n_arena)
         L = _table(lt_p, nL, _lib.LAYER_DT)
@@ -75,13 +75,44 @@ class FakeLib:
             bb = arena[int(r["bn_b_off"]): int(r["bn_b_off"]) + Cn] if r["bn_b_off"] >= 0 else None
             bns.append((bw, bb))
             rels.append(O.ORelation(remap[int(r["first"])], remap[int(r["second"])], len(bns) - 1))
+        if int(P["apply_only"]):
+            for r, rel in zip(R, rels):
+                S = arena[int(r["s_acc_off"]): int(r["s_acc_off"]) + int(r["channels"])].copy()
+                l1, l2 = layers[rel.first], layers[rel.second]
+                l1.w *= S.reshape(-1, 1, 1); l1.b *= S
+                for v in bns[rel.bn]:
+                    if v is not None:
+                        v *= S
+                G, gi, go = int(r["groups"]), int(r["gi"]), int(r["go"])
+                inv = (f32(1) / S).astype(f32)
+                for g in range(G):
+                    l2.w[g * go:(g + 1) * go] *= inv[g * gi:(g + 1) * gi].reshape(1, -1, 1)
+            res[0]["n_sweeps"] = 1; res[0]["converged"] = 1
+            return 0
         lo, hi = float(P["s_lo"]), float(P["s_hi"])
         # the product passes fp32-rounded bounds and their reciprocals; hand the oracle doubles that round to the same
-        n, diffs = O.cross_layer_equalization(
-            layers, bns, rels, s_range=(_unround(lo, float(P["inv_lo"])), _unround(hi, float(P["inv_hi"]))),
-            converge_thres=float(P["converge_thres"]), converge_count=int(P["converge_count"]),
-            signed=bool(P["signed_mode"]), eps=float(P["eps"]), max_sweeps=int(P["max_sweeps"]) or None,
-            sqrt_fn=self.sqrt_fn)
+        gs = np.ctypeslib.as_array((C.c_int32 * int(n_groups)).from_address(int(_val(gs_p)))) if _val(gs_p) else None
+        n, diffs = 0, []
+        for g in range(int(n_groups)):       # one oracle call per convergence group (= per model)
+            sel = [k for k, r in enumerate(R) if int(L[int(r["first"])]["group"]) == g]
+            if not sel:
+                continue
+            used_g = sorted({rels[k].first for k in sel} | {rels[k].second for k in sel})
+            rm = {li: j for j, li in enumerate(used_g)}
+            sub = [O.ORelation(rm[rels[k].first], rm[rels[k].second], rels[k].bn) for k in sel]
+            ng, dg = O.cross_layer_equalization(
+                [layers[li] for li in used_g], bns, sub,
+                s_range=(_unround(lo, float(P["inv_lo"])), _unround(hi, float(P["inv_hi"]))),
+                converge_thres=float(P["converge_thres"]), converge_count=int(P["converge_count"]),
+                signed=bool(P["signed_mode"]), eps=float(P["eps"]), max_sweeps=int(P["max_sweeps"]) or None,
+                sqrt_fn=self.sqrt_fn)
+            for k, sr in zip(sel, sub):
+                rels[k].S = sr.S
+            if gs is not None:
+                gs[g] = ng
+            if g == 0:
+                diffs = dg
+            n = max(n, ng)
         for r, rel in zip(R, rels):
             arena[int(r["s_acc_off"]): int(r["s_acc_off"]) + int(r["channels"])] = rel.S
         res[0]["n_sweeps"] = n
@@ -240,3 +271,11 @@ def install(monkeypatch, sqrt_fn=None):
     import dfq_b200.utils.quantize as q
     monkeypatch.setattr(q, "_dev_f32", lambda x: (x.contiguous(), True))
     return fake
+
+
+def install_plain(sqrt_fn=None):
+    """install() without pytest (spawned worker processes): returns the fake; patches stay for the process lifetime."""
+    class _MP:
+        def setattr(self, obj, name, value):
+            setattr(obj, name, value)
+    return install(_MP(), sqrt_fn)

@@ -39,7 +39,7 @@ def test_struct_mirrors_match_compiled_sizes():
 def test_struct_field_offsets_follow_the_header_order():
     """numpy's aligned layout must equal the C layout: check a few load-bearing offsets."""
     from dfq_b200 import _lib
-    assert _lib.LAYER_DT.fields["rows"][1] == 16 and _lib.LAYER_DT.fields["cmin_off"][1] == 40
+    assert _lib.LAYER_DT.fields["rows"][1] == 16 and _lib.LAYER_DT.fields["cmin_off"][1] == 48 and _lib.LAYER_DT.fields["group"][1] == 40
     assert _lib.RELATION_DT.fields["bn_w_off"][1] == 24 and _lib.RELATION_DT.fields["inv_off"][1] == 56
     assert _lib.CLE_PARAMS_DT.fields["converge_thres"][1] == 24 and _lib.CLE_PARAMS_DT.fields["max_sweeps"][1] == 36
     assert _lib.BC_LAYER_DT.fields["flags"][1] == 20 and _lib.BC_LAYER_DT.fields["expect_off"][1] == 24

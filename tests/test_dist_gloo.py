@@ -1,0 +1,89 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: chain building, LPT partition, the single all-gather of
+the scale vectors, replica replay, and the exact-mode sweep count.  The arithmetic is executed by tests/fakelib.py (the
+oracle); the -m gpu suite covers the kernels, and bench.py --gpus N the NCCL path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _worker(rank, world, port, mode, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import torch.nn as nn
+    import fakelib
+    from dfq_b200 import workload, dist as ddist
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    torch.set_num_threads(2)
+    fakelib.install_plain(fakelib.torch_sqrt)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        topo = workload.load_topology(os.path.join(GOLD, "topology_mobilenetv2.json"))
+        graph, bottoms, _ = workload.build_graph(topo, seed=0)
+        targ = [nn.Conv2d, nn.Linear]
+        LT.merge_batchnorm(None, graph, bottoms, targ)
+        rels = create_relation(graph, bottoms, targ)
+        info = ddist.sharded_cross_layer_equalization(graph, rels, targ, mode=mode)
+        keys = list(graph.keys())
+        out = {"sweeps": np.array(info["sweeps"]), "owner": np.array(info["owner"])}
+        for i, k in enumerate(keys):
+            if type(graph[k]) in targ:
+                out["w%d" % i] = graph[k].weight.detach().numpy()
+                if graph[k].bias is not None:
+                    out["b%d" % i] = graph[k].bias.detach().numpy()
+        for i, r in enumerate(rels):
+            out["S%d" % i] = r.S.numpy()
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+def _nw(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("mode", ["exact", "per_chain"])
+def test_two_rank_sharded_equalization(mode, tmp_path):
+    port = 29500 + (os.getpid() % 2000) + (7 if mode == "exact" else 0)
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    gold = np.load(os.path.join(GOLD, "ref_mobilenetv2.npz"))
+    # both ranks end with the same full model
+    assert set(r0.files) == set(r1.files)
+    assert set(r0["owner"].tolist()) == {0, 1}, "chains must be spread over both ranks"
+    for k in r0.files:
+        if k[0] in "wbS":
+            assert _nw(r0[k], r1[k]) < 1e-5, k
+    # ... and it is the reference's result
+    n_rel = gold["relations"].shape[0]
+    for i in range(n_rel):
+        assert _nw(r0["S%d" % i], gold["S_%d" % i]) < 1e-5, i
+    targets = gold["targets"]
+    for j, pos in enumerate(targets):
+        w = r0["w%d" % pos]
+        assert abs(np.abs(w).max() - gold["cle_w_absmax"][j]) <= 1e-5 * gold["cle_w_absmax"][j]
+        if "cle_bias_%d" % pos in gold.files and "b%d" % pos in r0.files:
+            assert _nw(r0["b%d" % pos], gold["cle_bias_%d" % pos]) < 1e-5
+    if mode == "exact":
+        assert int(r0["sweeps"]) == int(gold["n_sweeps"]) == int(r1["sweeps"])
+
+
+def test_partition_and_chains_are_deterministic():
+    from dfq_b200.dist import build_chains, partition_lpt, _replay_exit_rule
+    from dfq_b200.utils.relation import Relation
+    rels = [Relation("a", "b", "x"), Relation("b", "c", "y"), Relation("d", "e", "z"), Relation("c", "f", "w")]
+    assert build_chains(rels) == [[0, 1, 3], [2]]
+    assert partition_lpt([5, 3, 3, 2], 2) == [0, 1, 1, 0]
+    assert partition_lpt([1, 1, 1], 1) == [0, 0, 0]
+    # dfq.py:81-115 replay: stops when diff <= thres or after converge_count stagnant sweeps
+    assert _replay_exit_rule([1.0, 0.5, 1e-8], 2e-7, 20) == 3
+    assert _replay_exit_rule([1.0] * 30, 2e-7, 3) == 4

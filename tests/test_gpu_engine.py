@@ -215,3 +215,71 @@ def test_bias_correct_chain_matches_oracle():
     assert _normwise(b2.numpy(), b2_ref) < 1e-5
     assert _normwise(bn2[1].numpy(), fb2) < 1e-5
     assert _normwise(b3_gpu, b3_ref) < 1e-5
+
+
+def test_convergence_groups_equal_one_call_per_model():
+    """A batch of independent models in one launch (n_groups > 1): every group must stop on ITS exit rule, i.e. give
+    exactly what a separate cross_layer_equalization call per model gives (here: the oracle, model by model)."""
+    from dfq_b200.engine import Session
+    models = [[(32, 16, 3, 3), (24, 32, 3, 3)],
+              [(144, 24, 1, 1), (144, 1, 3, 3), (32, 144, 1, 1)],
+              [(64, 32, 3, 3), (64, 64, 3, 3), (48, 64, 3, 3)],
+              [(40, 512, 3, 3), (24, 40, 3, 3)]]
+    sess = Session()
+    rl, groups, refs, tensors = [], [], [], []
+    for m, shapes in enumerate(models):
+        ws, bs, bns = _chain_case(shapes, 200 + 10 * m)
+        layers = [O.OLayer(w.clone().numpy(), b.clone().numpy()) for w, b in zip(ws, bs)]
+        obns = [(a.clone().numpy(), b.clone().numpy()) for a, b in bns]
+        rels = [O.ORelation(i, i + 1, i) for i in range(len(shapes) - 1)]
+        n_ref, _ = O.cross_layer_equalization(layers, obns, rels)
+        ids = [sess.add_layer(w, b) for w, b in zip(ws, bs)]
+        offs = [(sess.bind(a), sess.bind(b)) for a, b in bns]
+        for i in range(len(shapes) - 1):
+            rl.append((ids[i], ids[i + 1], offs[i][0], offs[i][1])); groups.append(m)
+        refs.append((n_ref, layers, obns, rels)); tensors.append((ws, bs, bns))
+    sess.upload()
+    plan = sess.plan_cle(rl, groups=groups)
+    res = sess.run_cle_plan(plan)
+    sess.download()
+    assert list(res.group_sweeps) == [r[0] for r in refs], (list(res.group_sweeps), [r[0] for r in refs])
+    assert res.n_sweeps == max(r[0] for r in refs) and res.converged
+    for (n_ref, layers, obns, rels), (ws, bs, bns) in zip(refs, tensors):
+        for w, b, l in zip(ws, bs, layers):
+            assert np.array_equal(w.numpy(), l.w) and np.array_equal(b.numpy(), l.b)
+        for (a, b), (oa, ob) in zip(bns, obns):
+            assert np.array_equal(a.numpy(), oa) and np.array_equal(b.numpy(), ob)
+
+
+def test_large_stack_properties():
+    """Size-independent properties on a stack too large for the oracle to finish in seconds (BASELINE config 5 shapes):
+    every block converges in 2 sweeps; equalization preserves the function of each pair up to rounding
+    (W1[c]*W2[:,c] products are invariant: s * 1/s); re-running on the result is a fixed point in one more sweep."""
+    from dfq_b200.engine import Session
+    from dfq_b200.workload import DeviceStack
+    sess = Session()
+    st = DeviceStack(sess, 16, 512, 3, seed=5)
+    st.generate()
+    C, N = 512, st.N
+    w1_before = sess.view(sess.layer(st.layers[0])["w_off"], N).clone().view(C, -1)
+    w2_before = sess.view(sess.layer(st.layers[1])["w_off"], N).clone().view(C, C, 9)
+    sess.run_bn_fold(st.fold_plan)
+    f1 = sess.view(sess.layer(st.layers[0])["w_off"], N).clone().view(C, -1)
+    f2 = sess.view(sess.layer(st.layers[1])["w_off"], N).clone().view(C, C, 9)
+    res = sess.run_cle_plan(st.cle_plan)
+    assert res.converged and set(int(x) for x in res.group_sweeps) == {2}, res.group_sweeps
+    e1 = sess.view(sess.layer(st.layers[0])["w_off"], N).view(C, -1)
+    e2 = sess.view(sess.layer(st.layers[1])["w_off"], N).view(C, C, 9)
+    S = sess.view(st.cle_plan["s_offs"][0], C)
+    # rows scaled by S, columns by 1/S (up to two roundings per sweep)
+    assert torch.allclose(e1, f1 * S.view(-1, 1), rtol=1e-6, atol=0)
+    assert torch.allclose(e2, f2 / S.view(1, -1, 1), rtol=1e-6, atol=0)
+    # equalized: per-channel ranges of the pair agree
+    r1 = e1.max(1)[0] - e1.min(1)[0]
+    r2 = e2.amax((0, 2)) - e2.amin((0, 2))
+    assert torch.allclose(r1, r2, rtol=1e-5)
+    # idempotence: one more run changes (almost) nothing and stops after its first sweep
+    before = sess.view(st.w_begin, 2 * N).clone()
+    res2 = sess.run_cle_plan(st.cle_plan)
+    assert int(res2.group_sweeps.max()) == 1
+    assert torch.allclose(sess.view(st.w_begin, 2 * N), before, rtol=1e-6, atol=0)

@@ -1,0 +1,150 @@
+"""-m gpu: the drop-in entry points (merge_batchnorm -> create_relation -> cross_layer_equalization -> bias_correction
+-> quantize_targ_layer) on seeded models of the reference's architectures, real CUDA library vs
+
+  (1) the same host code executed with the numpy oracle (tests/fakelib.py): bit-exact for BN fold, equalization
+      (weights, biases, fake_weight/fake_bias, S, sweep count) and the 8-bit weight codes; 1e-5 normwise for bias
+      correction;
+  (2) the committed fixtures produced by the reference itself (tests/golden/ref_*.npz): 1e-5 normwise up to the
+      equalization, relaxed downstream (the reference's host sqrt is not correctly rounded and bias correction is
+      ill-conditioned in the last bit of the weights).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import fakelib
+from dfq_b200 import workload
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TARG = [nn.Conv2d, nn.Linear]
+
+
+def _nw(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _pipeline(name, seed, stages):
+    from dfq_b200 import dfq
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    topo = workload.load_topology(os.path.join(GOLD, "topology_%s.json" % name))
+    graph, bottoms, _ = workload.build_graph(topo, seed=seed)
+    snaps = {}
+
+    def snap(tag):
+        d = {}
+        for i, k in enumerate(graph):
+            m = graph[k]
+            if type(m) in TARG:
+                d["w%d" % i] = m.weight.detach().cpu().numpy().copy()
+                if m.bias is not None:
+                    d["b%d" % i] = m.bias.detach().cpu().numpy().copy()
+            if hasattr(m, "fake_bias") and not isinstance(m, str):
+                d["fb%d" % i] = m.fake_bias.cpu().numpy().copy(); d["fw%d" % i] = m.fake_weight.cpu().numpy().copy()
+        snaps[tag] = d
+
+    LT.merge_batchnorm(None, graph, bottoms, TARG); snap("fold")
+    rels = create_relation(graph, bottoms, TARG, delete_single=(name == "ssd"))
+    dfq.cross_layer_equalization(graph, rels, TARG, converge_thres=2e-7); snap("cle")
+    snaps["n_sweeps"] = dfq.cross_layer_equalization.last_result.n_sweeps
+    snaps["S"] = [r.S.cpu().numpy().copy() for r in rels]
+    if "bc" in stages:
+        dfq.bias_correction(graph, bottoms, TARG); snap("bc")
+    if "q" in stages:
+        LT.quantize_targ_layer(graph, 8, 16, TARG); snap("q")
+    return snaps, graph, rels
+
+
+@pytest.mark.parametrize("name,seed", [("resnet18", 3), ("mobilenetv2", 0), ("deeplab", 5), ("ssd", 7)])
+def test_pipeline_cuda_vs_oracle_executor(name, seed, monkeypatch):
+    stages = ("bc", "q")
+    real, _, _ = _pipeline(name, seed, stages)
+    with monkeypatch.context() as mp:
+        fakelib.install(mp)
+        ref, _, _ = _pipeline(name, seed, stages)
+    assert real["n_sweeps"] == ref["n_sweeps"]
+    for tag in ("fold", "cle"):
+        for k, v in ref[tag].items():
+            assert np.array_equal(real[tag][k], v), "%s %s %s: normwise %g" % (name, tag, k, _nw(real[tag][k], v))
+    for a, b in zip(real["S"], ref["S"]):
+        assert np.array_equal(a, b)
+    for k, v in ref["bc"].items():
+        assert _nw(real["bc"][k], v) < 1e-5, (name, "bc", k, _nw(real["bc"][k], v))
+    for k, v in ref["q"].items():
+        if k.startswith("w"):
+            assert np.array_equal(real["q"][k], v), (name, "q", k)        # weights untouched by BC: codes bit-exact
+        else:
+            assert _nw(real["q"][k], v) < 1e-4, (name, "q", k)
+
+
+@pytest.mark.parametrize("name,seed", [("resnet18", 3), ("mobilenetv2", 0)])
+def test_pipeline_cuda_vs_reference_fixture(name, seed):
+    gold = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    real, graph, rels = _pipeline(name, seed, ("bc",))
+    keys = list(graph.keys())
+    assert real["n_sweeps"] == int(gold["n_sweeps"])
+    assert np.array_equal(np.array([[keys.index(a), keys.index(b), keys.index(c)] for a, b, c in (r.get_idxs() for r in rels)]),
+                          gold["relations"])
+    for i, S in enumerate(real["S"]):
+        assert _nw(S, gold["S_%d" % i]) < 1e-5
+    tl = [i for i, k in enumerate(keys) if type(graph[k]) in TARG]
+    for tag in ("fold", "cle"):
+        for j, i in enumerate(tl):
+            w = real[tag]["w%d" % i]
+            assert abs(np.abs(w).max() - gold[tag + "_w_absmax"][j]) <= 1e-5 * gold[tag + "_w_absmax"][j]
+            if "%s_bias_%d" % (tag, i) in gold.files:
+                assert _nw(real[tag]["b%d" % i], gold["%s_bias_%d" % (tag, i)]) < 1e-5
+        for k in real[tag]:
+            if k.startswith("fb"):
+                assert _nw(real[tag][k], gold["%s_fb_%s" % (tag, k[2:])]) < 1e-5
+                assert _nw(real[tag]["fw" + k[2:]], gold["%s_fw_%s" % (tag, k[2:])]) < 1e-5
+    for j, i in enumerate(tl):
+        if "bc_bias_%d" % i in gold.files:
+            assert _nw(real["bc"]["b%d" % i], gold["bc_bias_%d" % i]) < 5e-2
+
+
+def test_quant_modules_forward_on_gpu_matches_torch_eager_reference_chain():
+    """Activations: the reference runs quantize.py:70-74 on CUDA tensors, where PyTorch's div_(python_float) is a
+    multiply by the fp32 reciprocal.  The kernel must match that op chain executed by PyTorch CUDA eager bit for bit."""
+    from dfq_b200.utils import quantize as Q
+    torch.manual_seed(0)
+    x = torch.randn(64, 32, 28, 28, device="cuda") * 2
+    for bits, mn, mx in ((8, -2.11790393, 2.64), (8, 0.0, 5.3), (4, -1.0, 1.0), (16, -3.3, 7.7)):
+        qmax = 2. ** bits - 1.
+        scale = max((mx - mn) / qmax, 1e-8)
+        ref = x.clone().add_(-mn).div_(scale).clamp_(0., qmax).round_().mul_(scale).add_(mn)
+        got = Q.quantize(x, bits, mn, mx)
+        assert torch.equal(got, ref), (bits, mn, mx, (got != ref).sum().item())
+    # observer in eval mode with set ranges; no host sync is needed but the result is the same
+    qm = Q.QuantMeasure().cuda().eval()
+    qm.running_min.fill_(-2.11790393); qm.running_max.fill_(2.64)
+    mn, mx = float(qm.running_min), float(qm.running_max)
+    scale = max((mx - mn) / 255., 1e-8)
+    ref = x.clone().add_(-mn).div_(scale).clamp_(0., 255.).round_().mul_(scale).add_(mn)
+    assert torch.equal(qm(x), ref)
+    # update_stat: running range follows the per-sample extrema (quantize.py:103-107)
+    qm2 = Q.QuantMeasure(True).cuda().eval()
+    _ = qm2(x)
+    want_max = x.view(64, -1).max(-1)[0].mean(); want_min = x.view(64, -1).min(-1)[0].mean()
+    assert abs(float(qm2.running_max) - float(want_max)) <= 1e-6 * abs(float(want_max))
+    assert abs(float(qm2.running_min) - float(want_min)) <= 1e-6 * abs(float(want_min))
+    # Quant layers run and agree with the eager chain built from their own quantized operands
+    conv = Q.QuantConv2d(32, 16, 3, padding=1).cuda().eval()
+    conv.quant.running_min.fill_(-6.); conv.quant.running_max.fill_(6.)
+    y = conv(x[:4])
+    w = conv.weight.detach()
+    wmn, wmx = float(w.min()), float(w.max()); ws = max((wmx - wmn) / 255., 1e-8)
+    qw = w.clone().add_(-wmn).div_(ws).clamp_(0., 255.).round_().mul_(ws).add_(wmn)
+    xs = max(12. / 255., 1e-8)
+    qx = x[:4].clone().add_(6.).div_(xs).clamp_(0., 255.).round_().mul_(xs).add_(-6.)
+    b = conv.bias.detach()
+    bmn, bmx = b.min(), b.max()
+    bs = (bmx - bmn) / 65535.
+    qb = b.clone().add_(-bmn).div_(bs).clamp_(0., 65535.).round_().mul_(bs).add_(bmn)
+    ref = torch.nn.functional.conv2d(qx, qw, qb, 1, 1)
+    assert torch.allclose(y, ref, rtol=1e-5, atol=1e-5)
