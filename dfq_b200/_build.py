@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libdfq_sm100.so")
+LIB = os.environ.get("DFQ_LIB_OUT") or os.path.join(HERE, "libdfq_sm100.so")
 SOURCES = ["tensor_ops.cu", "cle_engine.cu", "passes.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dfq_b200.h")]
 
@@ -34,7 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    extra = os.environ.get("DFQ_NVCC_DEFS", "").split()      # tuning experiments, e.g. -DDFQ_PIPE_STAGES=5 -DDFQ_CTAS=2
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfq_sm100.so")
+LIB_PATH = os.environ.get("DFQ_LIB") or os.path.join(_HERE, "libdfq_sm100.so")   # DFQ_LIB: a tuning build
 
 ABI_VERSION = 1
 
@@ -93,7 +93,7 @@ SIGNATURES = {
     "dfq_bias_correct": [_PF, _I64, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, _I32, C.c_void_p, _I32, _I32, _ST],
     "dfq_quantize_tensors": [_PF, _I64, C.c_void_p, _I32, C.c_int, _ST],
     "dfq_minmax": [_PF, _I64, _PF, _ST],
-    "dfq_quant_dequant": [_PF, _PF, _I64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _PF, _ST],
+    "dfq_quant_dequant": [_PF, _PF, _I64, C.c_float, C.c_double, C.c_float, C.c_float, C.c_int, _PF, _ST],
     "dfq_quant_dequant_dev": [_PF, _PF, _I64, _PF, _PF, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _ST],
     "dfq_act_minmax_per_sample": [_PF, _I64, _I64, _PF, _PF, _ST],
     "dfq_observer_update": [_PF, _PF, _PF, C.c_int, C.c_float, _ST],

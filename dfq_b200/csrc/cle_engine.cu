@@ -22,10 +22,14 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "common.cuh"
+#include "rowpipe.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -35,6 +39,10 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kScanRows = 32;      // rows per column-scan tile
 constexpr int kScanCols = 2048;    // columns kept in shared memory by a scan tile
+#ifndef DFQ_INV_CACHE
+#define DFQ_INV_CACHE 2044
+#endif
+constexpr int kInvCache = DFQ_INV_CACHE;    // reciprocal scales of a layer's input columns cached in shared memory
 
 // Convergence state of one GROUP of chains.  The reference's exit rule (dfq.py:81-115) is evaluated per model: one
 // group.  A batch of independent models (the synthetic stack: every block is its own model) is calibrated in one
@@ -50,30 +58,18 @@ struct GroupState {
 struct CleCtl {
   int active[2];   // groups still iterating, double-buffered by sweep parity
   double diffs[64];  // diff_tmp per sweep of group 0
+  unsigned long long t_ns[16];  // %globaltimer at phase boundaries (block 0), printed when DFQ_TRACE is set
+  int grid, per_sm;
 };
 
-enum RowKind { RK_W4_1 = 0, RK_W4_4, RK_W4_8, RK_C4_8, RK_WS_1, RK_WS_8, RK_GENERIC };
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
-__host__ __device__ inline int row_kind(int64_t w_off, int row_len) {
-  const bool v4 = (row_len % 4 == 0) && (w_off % 4 == 0);
-  if (v4) {
-    if (row_len <= 128) return RK_W4_1;
-    if (row_len <= 512) return RK_W4_4;
-    if (row_len <= 1024) return RK_W4_8;
-    if (row_len <= 8192) return RK_C4_8;
-    return RK_GENERIC;
-  }
-  if (row_len <= 32) return RK_WS_1;
-  if (row_len <= 256) return RK_WS_8;
-  return RK_GENERIC;
-}
-__host__ __device__ inline int rows_per_tile(int kind) {
-  return (kind == RK_C4_8 || kind == RK_GENERIC) ? 1 : kWarps;
-}
-__host__ __device__ inline int pass_tiles(const DfqLayer& l) {
-  const int rpt = rows_per_tile(row_kind(l.w_off, l.cols * l.kk));
-  return (l.rows + rpt - 1) / rpt;
-}
+// pass tiles: contiguous chunks of rows moved by the RowPipe (rowpipe.cuh)
+__host__ __device__ inline int pass_tiles(const DfqLayer& l) { return pipe_tiles(l.rows, l.cols * l.kk); }
 __host__ __device__ inline int scan_tiles(int G, int go) {
   return G * ((go + kScanRows - 1) / kScanRows);
 }
@@ -94,6 +90,7 @@ struct RowCtx {
   float* own_cmax_wr;
   double inv_n;
   int first_sweep;
+  int inv_cached;        // 1: inv_in[0 .. cols) of the (single) input group is cached in shared memory
 };
 
 // dfq.py:58-59 + :73.  Returns s; *inv is the factor applied to the columns of the second layer.
@@ -139,9 +136,8 @@ __device__ __forceinline__ void cta_minmax(float& mn, float& mx, float* red, int
 
 // All threads of the row's group call this with the reduced row extrema; the leader publishes.
 __device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCleParams& P, int o,
-                                                   float mn, float mx, bool leader) {
+                                                   float mn, float mx, float cmn, float cmx, bool leader) {
   const float r1 = range_of(mn, mx, P.signed_mode);
-  const float cmn = __ldcg(c.cmin_rd + o), cmx = __ldcg(c.cmax_rd + o);
   const float r2 = range_of(cmn, cmx, P.signed_mode);
   float inv;
   float s;
@@ -170,103 +166,133 @@ __device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCle
   return s;
 }
 
-// One row, held in registers between the range and the rescale: NV 128-bit (or 32-bit) loads per
-// thread are all in flight before the first use.  TPR = threads per row (32: warp, 256: CTA).
-template <int NV, int TPR, bool VEC>
-__device__ __forceinline__ void cle_row(const RowCtx& c, const DfqCleParams& P, int o, int lane,
-                                        float* red, int& parity, double& dacc) {
-  float* rowp = c.w + (size_t)o * c.row_len;
-  const int cbase = c.inv_in ? (o / c.in_go) * c.in_gi : 0;
-  const bool leader = (lane == 0);
-  float dsum = 0.f;
+// ------------------------------------------------------------------------------------------------------------
+// One tile (nrows consecutive rows of one layer) resident in shared memory: range reduction, s, rescale IN PLACE.
+// TPR = threads per row: kThreads (the whole CTA on one long row, block reduction) or 32 (one warp per row).
+// ------------------------------------------------------------------------------------------------------------
+// How the reciprocal scales of the in-relation map onto the elements of a row (decided once per layer):
+enum InMode { IN_NONE = 0, IN_UNIFORM, IN_KK1, IN_KK9, IN_GENERIC };
+
+// Column-scale four consecutive elements e .. e+3 of a row.  `inv` points at the 1/s of this row's input group
+// (shared-memory cache for IN_KK1 / IN_KK9, global memory for IN_GENERIC); `u` is the row-uniform factor (IN_UNIFORM).
+template <int MODE>
+__device__ __forceinline__ float4 in_scale4(float4 t, int e, const float* __restrict__ inv, float u, int kk) {
+  if (MODE == IN_UNIFORM) {
+    t.x = __fmul_rn(t.x, u); t.y = __fmul_rn(t.y, u); t.z = __fmul_rn(t.z, u); t.w = __fmul_rn(t.w, u);
+  } else if (MODE == IN_KK1) {
+    const float4 f = *(const float4*)(inv + e);            // e % 4 == 0 and the cache is 16-byte aligned
+    t.x = __fmul_rn(t.x, f.x); t.y = __fmul_rn(t.y, f.y); t.z = __fmul_rn(t.z, f.z); t.w = __fmul_rn(t.w, f.w);
+  } else if (MODE == IN_KK9) {
+    const int q = e / 9, r = e - 9 * q;                      // four consecutive elements span at most two columns
+    const float f0 = inv[q], f1 = inv[q + 1 - (r < 6 ? 1 : 0)];   // second column only when r + 3 >= 9
+    t.x = __fmul_rn(t.x, f0);
+    t.y = __fmul_rn(t.y, r + 1 >= 9 ? f1 : f0);
+    t.z = __fmul_rn(t.z, r + 2 >= 9 ? f1 : f0);
+    t.w = __fmul_rn(t.w, r + 3 >= 9 ? f1 : f0);
+  } else if (MODE == IN_GENERIC) {
+    t.x = __fmul_rn(t.x, __ldcg(inv + (e) / kk));
+    t.y = __fmul_rn(t.y, __ldcg(inv + (e + 1) / kk));
+    t.z = __fmul_rn(t.z, __ldcg(inv + (e + 2) / kk));
+    t.w = __fmul_rn(t.w, __ldcg(inv + (e + 3) / kk));
+  }
+  return t;
+}
+template <int MODE>
+__device__ __forceinline__ float in_scale1(float t, int e, const float* __restrict__ inv, float u, int kk) {
+  if (MODE == IN_UNIFORM) return __fmul_rn(t, u);
+  if (MODE == IN_KK1) return __fmul_rn(t, inv[e]);
+  if (MODE == IN_KK9) return __fmul_rn(t, inv[e / 9]);
+  if (MODE == IN_GENERIC) return __fmul_rn(t, __ldcg(inv + e / kk));
+  return t;
+}
+
+// One row resident in shared memory: [range reduction -> s] (HAS_OUT) then rescale IN PLACE, accumulating |new - old|.
+// Everything the loops need is copied into registers first: `row` stores could alias the context in shared memory,
+// which would force the compiler to reload it after every store.
+template <int TPR, int MODE, bool HAS_OUT>
+__device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams& P, float* __restrict__ row, int o, int lane,
+                                             const float* __restrict__ s_inv, float* red, int& parity, double& dacc) {
+  const int n = c.row_len, kk = c.kk;
+  const bool vec = ((n & 3) == 0);
+  const double inv_n = c.inv_n;
+  const float* inv = nullptr;
+  float u = 1.f;
+  if (MODE == IN_UNIFORM) u = __ldcg(c.inv_in + (o / c.in_go) * c.in_gi);
+  else if (MODE == IN_KK1 || MODE == IN_KK9) inv = s_inv;
+  else if (MODE == IN_GENERIC) inv = c.inv_in + (o / c.in_go) * c.in_gi;
   float s = 1.f;
-  if (VEC) {
-    const int n4 = c.row_len >> 2;
-    float4 u[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int i4 = lane + i * TPR;
-      if (i4 < n4) u[i] = ldg_stream((const float4*)rowp + i4);
-    }
-    if (c.has_out) {
-      float mn = DFQ_INF, mx = -DFQ_INF;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int i4 = lane + i * TPR;
-        if (i4 < n4) {
-          float4 t = u[i];
-          if (c.inv_in) {
-            const int e = i4 * 4;
-            t.x = __fmul_rn(t.x, __ldcg(c.inv_in + cbase + col_of(e, c.kk)));
-            t.y = __fmul_rn(t.y, __ldcg(c.inv_in + cbase + col_of(e + 1, c.kk)));
-            t.z = __fmul_rn(t.z, __ldcg(c.inv_in + cbase + col_of(e + 2, c.kk)));
-            t.w = __fmul_rn(t.w, __ldcg(c.inv_in + cbase + col_of(e + 3, c.kk)));
-          }
-          mn = fminf(mn, fminf(fminf(t.x, t.y), fminf(t.z, t.w)));
-          mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
-        }
+  if (HAS_OUT) {
+    const float cmn = __ldcg(c.cmin_rd + o), cmx = __ldcg(c.cmax_rd + o);   // in flight during the reduction
+    float mn = DFQ_INF, mx = -DFQ_INF;
+    if (vec) {
+      const float4* r4 = (const float4*)row;
+      const int n4 = n >> 2;
+#pragma unroll 2
+      for (int i4 = lane; i4 < n4; i4 += TPR) {
+        const float4 t = in_scale4<MODE>(r4[i4], i4 * 4, inv, u, kk);
+        mn = fminf(mn, fminf(fminf(t.x, t.y), fminf(t.z, t.w)));
+        mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
       }
-      if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
-      else cta_minmax(mn, mx, red, parity);
-      s = solve_and_publish(c, P, o, mn, mx, leader);
-    }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int i4 = lane + i * TPR;
-      if (i4 < n4) {
-        float4 t = u[i];
-        if (c.inv_in) {
-          const int e = i4 * 4;
-          t.x = __fmul_rn(t.x, __ldcg(c.inv_in + cbase + col_of(e, c.kk)));
-          t.y = __fmul_rn(t.y, __ldcg(c.inv_in + cbase + col_of(e + 1, c.kk)));
-          t.z = __fmul_rn(t.z, __ldcg(c.inv_in + cbase + col_of(e + 2, c.kk)));
-          t.w = __fmul_rn(t.w, __ldcg(c.inv_in + cbase + col_of(e + 3, c.kk)));
-        }
-        if (c.has_out) {
-          t.x = __fmul_rn(t.x, s); t.y = __fmul_rn(t.y, s);
-          t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s);
-        }
-        stg_stream((float4*)rowp + i4, t);
-        dsum += fabsf(__fsub_rn(t.x, u[i].x)) + fabsf(__fsub_rn(t.y, u[i].y)) +
-                fabsf(__fsub_rn(t.z, u[i].z)) + fabsf(__fsub_rn(t.w, u[i].w));
+    } else {
+      for (int e = lane; e < n; e += TPR) {
+        const float t = in_scale1<MODE>(row[e], e, inv, u, kk);
+        mn = fminf(mn, t); mx = fmaxf(mx, t);
       }
+    }
+    if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
+    else cta_minmax(mn, mx, red, parity);
+    s = solve_and_publish(c, P, o, mn, mx, cmn, cmx, lane == 0);
+  }
+  float dsum = 0.f;
+  if (vec) {
+    float4* r4 = (float4*)row;
+    const int n4 = n >> 2;
+#pragma unroll 2
+    for (int i4 = lane; i4 < n4; i4 += TPR) {
+      const float4 v = r4[i4];
+      float4 t = in_scale4<MODE>(v, i4 * 4, inv, u, kk);
+      if (HAS_OUT) { t.x = __fmul_rn(t.x, s); t.y = __fmul_rn(t.y, s); t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s); }
+      r4[i4] = t;
+      dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
     }
   } else {
-    const int n = c.row_len;
-    float u[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int e = lane + i * TPR;
-      if (e < n) u[i] = ldg_stream1(rowp + e);
-    }
-    if (c.has_out) {
-      float mn = DFQ_INF, mx = -DFQ_INF;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int e = lane + i * TPR;
-        if (e < n) {
-          float t = u[i];
-          if (c.inv_in) t = __fmul_rn(t, __ldcg(c.inv_in + cbase + col_of(e, c.kk)));
-          mn = fminf(mn, t); mx = fmaxf(mx, t);
-        }
-      }
-      if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
-      else cta_minmax(mn, mx, red, parity);
-      s = solve_and_publish(c, P, o, mn, mx, leader);
-    }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int e = lane + i * TPR;
-      if (e < n) {
-        float t = u[i];
-        if (c.inv_in) t = __fmul_rn(t, __ldcg(c.inv_in + cbase + col_of(e, c.kk)));
-        if (c.has_out) t = __fmul_rn(t, s);
-        stg_stream1(rowp + e, t);
-        dsum += fabsf(__fsub_rn(t, u[i]));
-      }
+    for (int e = lane; e < n; e += TPR) {
+      const float v = row[e];
+      float t = in_scale1<MODE>(v, e, inv, u, kk);
+      if (HAS_OUT) t = __fmul_rn(t, s);
+      row[e] = t;
+      dsum += fabsf(__fsub_rn(t, v));
     }
   }
-  dacc += (double)dsum * c.inv_n;
+  dacc += (double)dsum * inv_n;
+}
+
+template <int MODE, bool HAS_OUT>
+__device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams& P, float* buf, int row0, int nrows,
+                                              const float* s_inv, float* red, int& parity, double& dacc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (nrows == 1) {
+    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, row0, threadIdx.x, s_inv, red, parity, dacc);
+  } else {
+    const int row_len = c.row_len;
+    for (int r = warp; r < nrows; r += kWarps)
+      cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, row0 + r, lane, s_inv, red, parity, dacc);
+  }
+}
+
+__device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParams& P, int in_mode, float* buf, int row0,
+                                              int nrows, const float* s_inv, float* red, int& parity, double& dacc) {
+#define DFQ_TILE(M)                                                                              \
+  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc);       \
+  else cle_tile_rows<M, false>(c, P, buf, row0, nrows, s_inv, red, parity, dacc);
+  switch (in_mode) {
+    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc); break;
+    case IN_UNIFORM: DFQ_TILE(IN_UNIFORM) break;
+    case IN_KK1: DFQ_TILE(IN_KK1) break;
+    case IN_KK9: DFQ_TILE(IN_KK9) break;
+    default: DFQ_TILE(IN_GENERIC) break;
+  }
+#undef DFQ_TILE
 }
 
 // Any row length / alignment: CTA per row, the row is read twice (second read is an L2 hit).
@@ -283,7 +309,7 @@ __device__ __forceinline__ void cle_row_generic(const RowCtx& c, const DfqClePar
       mn = fminf(mn, t); mx = fmaxf(mx, t);
     }
     cta_minmax(mn, mx, red, parity);
-    s = solve_and_publish(c, P, o, mn, mx, threadIdx.x == 0);
+    s = solve_and_publish(c, P, o, mn, mx, __ldcg(c.cmin_rd + o), __ldcg(c.cmax_rd + o), threadIdx.x == 0);
   }
   float dsum = 0.f;
   for (int e = threadIdx.x; e < c.row_len; e += kThreads) {
@@ -305,12 +331,13 @@ __device__ __forceinline__ void make_ctx(RowCtx& c, float* arena, const DfqLayer
   c.inv_n = 1.0 / ((double)l.rows * (double)c.row_len);
   c.first_sweep = (sweep == 0);
   const int rd = sweep & 1, wr = rd ^ 1;
-  c.inv_in = nullptr; c.in_gi = 1; c.in_go = 1;
+  c.inv_in = nullptr; c.in_gi = 1; c.in_go = 1; c.inv_cached = 0;
   c.own_cmin_wr = c.own_cmax_wr = nullptr;
   if (l.rel_in >= 0) {
     const DfqRelation r = R[l.rel_in];
     c.inv_in = arena + r.inv_off;
     c.in_gi = r.gi; c.in_go = r.go;
+    c.inv_cached = (r.groups == 1 && l.cols <= kInvCache) ? 1 : 0;
     if (l.col_mode == 1 && l.rel_out >= 0) {
       c.own_cmin_wr = arena + l.cmin_off + (size_t)wr * r.channels;
       c.own_cmax_wr = arena + l.cmax_off + (size_t)wr * r.channels;
@@ -390,7 +417,47 @@ __device__ __forceinline__ void reset_cols(float* arena, const DfqLayer& l, cons
   for (int j = threadIdx.x; j < r.channels; j += kThreads) { __stcg(a + j, DFQ_INF); __stcg(b + j, -DFQ_INF); }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+// Walks the pass tiles of this CTA's span in one step, skipping the layers of converged groups.  The producer thread
+// keeps a second copy kPipeStages-1 tiles ahead; both copies see the same `done` flags (they only change at sweep end).
+struct PassIter {
+  const long long* ptr; const int* step_layers; const DfqLayer* L; const GroupState* G;
+  int q, q_begin, q_end;
+  TileCursor cur;
+  int q_live;   // last task whose group was checked and found still iterating (one uncached read per layer, not per tile)
+  __device__ __forceinline__ void settle() {
+    while (cur.valid()) {
+      while (q + 1 < q_end && ptr[q + 1] <= cur.t) ++q;
+      if (q != q_live) {
+        if (*((volatile const int*)&G[L[step_layers[q]].group].done)) { cur.seek(ptr[q + 1]); continue; }
+        q_live = q;
+      }
+      break;
+    }
+  }
+  __device__ __forceinline__ void start(const long long* p, const int* sl, const DfqLayer* L_, const GroupState* G_, int qb, int qe) {
+    ptr = p; step_layers = sl; L = L_; G = G_; q_begin = qb; q_end = qe; q_live = -1;
+    cur.init(p[qb], p[qe]);
+    q = cur.valid() ? find_task(p, qb, qe, cur.t) : qb;
+    settle();
+  }
+  __device__ __forceinline__ bool valid() const { return cur.valid(); }
+  __device__ __forceinline__ void next() { cur.next(); settle(); }
+  __device__ __forceinline__ void fill(TileDesc& d, float* arena) const {
+    const int li = step_layers[q];
+    const DfqLayer l = L[li];
+    const int row_len = l.cols * l.kk;
+    const int rpt = pipe_rows_per_tile(row_len);
+    d.task = li;
+    d.row0 = (int)(cur.t - ptr[q]) * rpt;
+    d.nrows = min(rpt, l.rows - d.row0);
+    d.floats = d.nrows * row_len;
+    d.gptr = arena + l.w_off + (size_t)d.row0 * row_len;
+    if (row_len > kStageFloats) d.kind = TK_DIRECT;
+    else d.kind = (((((uintptr_t)d.gptr) & 15) == 0) && ((d.floats & 3) == 0)) ? TK_BULK : TK_PLAIN;
+  }
+};
+
+__global__ void __launch_bounds__(kThreads, kPipeCtas)
 k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelation* __restrict__ R, int nR,
              const int* __restrict__ step_ptr, const int* __restrict__ step_layers, int n_steps,
              const int* __restrict__ step_rescan, const long long* __restrict__ pass_ptr,
@@ -398,13 +465,22 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
              DfqCleParams P, CleCtl* ctl, GroupState* G, int nG) {
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[2 * 2 * kWarps];
-  __shared__ float smin[kScanCols];
-  __shared__ float smax[kScanCols];
+  __shared__ __align__(16) float s_inv[kInvCache + 4];   // 1/s of the current layer's input columns
   __shared__ double dred[kWarps];
   __shared__ RowCtx sctx;
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  // the column-scan scratch aliases the (idle) first pipe stage: scans and passes never overlap
+  float* smin = (float*)pipe_smem;
+  float* smax = smin + kScanCols;
+  static_assert(2 * kScanCols * sizeof(float) <= (size_t)kStageBytes, "scan scratch must fit one stage");
+  RowPipe pipe;
+  pipe.init(pipe_smem);
   int parity = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  int tmark = 0;
+  auto mark = [&]() { if (blockIdx.x == 0 && threadIdx.x == 0 && tmark < 16) ctl->t_ns[tmark] = gtimer(); tmark++; };
+  mark();
   // ---- phase 0: column extrema of every `second` layer (buffer 0) -----------------------------
   for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) G[g].diff = 10.0;   // dfq.py:81
   for (int li = blockIdx.x; li < nL; li += gridDim.x)
@@ -418,6 +494,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
     }
   }
   grid.sync();
+  mark();
 
   for (int sweep = 0;; ++sweep) {
     const int slot = sweep % 3;
@@ -439,43 +516,54 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
         }
         dacc = 0.0;
       };
-      const TileSpan sp = tile_span(pass_ptr, step_ptr[p], step_ptr[p + 1]);
-      for (int q = sp.q; q < step_ptr[p + 1] && pass_ptr[q] < sp.hi; ++q) {
-        const int li = step_layers[q];
-        const long long base = pass_ptr[q];
-        const int t0 = (int)(max(sp.lo, base) - base), t1 = (int)(min(sp.hi, pass_ptr[q + 1]) - base);
-        if (t1 <= t0) continue;
-        const int g = L[li].group;
-        if (*((volatile int*)&G[g].done)) continue;          // this model has converged: its weights are final
-        if (g != cur_g) { flush(); cur_g = g; }
-        __syncthreads();                       // previous layer's tiles are done with sctx
-        if (threadIdx.x == 0) make_ctx(sctx, arena, L, R, li, sweep);
-        __syncthreads();
-        const RowCtx& c = sctx;
-        const int kind = row_kind(L[li].w_off, c.row_len);
-        const int rpt = rows_per_tile(kind);
-        if (L[li].col_mode == 2 && L[li].rel_in >= 0 && t0 == 0)
-          reset_cols(arena, L[li], R[L[li].rel_in], (sweep & 1) ^ 1);
-        for (int t = t0; t < t1; ++t) {
-          if (rpt == 1) {
-            if (kind == RK_C4_8) cle_row<8, kThreads, true>(c, P, t, threadIdx.x, red, parity, dacc);
-            else cle_row_generic(c, P, t, red, parity, dacc);
-          } else {
-            const int o = t * kWarps + warp;
-            if (o < c.rows) {
-              switch (kind) {
-                case RK_W4_1: cle_row<1, 32, true>(c, P, o, lane, red, parity, dacc); break;
-                case RK_W4_4: cle_row<4, 32, true>(c, P, o, lane, red, parity, dacc); break;
-                case RK_W4_8: cle_row<8, 32, true>(c, P, o, lane, red, parity, dacc); break;
-                case RK_WS_1: cle_row<1, 32, false>(c, P, o, lane, red, parity, dacc); break;
-                default: cle_row<8, 32, false>(c, P, o, lane, red, parity, dacc); break;
-              }
-            }
+      PassIter it;
+      it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
+      PassIter ahead = it;
+      TileDesc nd;
+      if (threadIdx.x == 0)
+        for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd, arena); pipe.issue(nd); ahead.next(); }
+      int cur_li = -1, in_mode = IN_NONE;
+      while (it.valid()) {
+        const int sidx = pipe.acquire();
+        const TileDesc d = pipe.desc[sidx];
+        if (d.task != cur_li) {
+          cur_li = d.task;
+          const int g = L[cur_li].group;
+          if (g != cur_g) { flush(); cur_g = g; }
+          __syncthreads();                       // everyone is done with the previous layer's context
+          if (threadIdx.x == 0) make_ctx(sctx, arena, L, R, cur_li, sweep);
+          __syncthreads();
+          if (sctx.inv_in == nullptr) in_mode = IN_NONE;
+          else if (sctx.cols == 1) in_mode = IN_UNIFORM;
+          else if (sctx.inv_cached && sctx.kk == 1) in_mode = IN_KK1;
+          else if (sctx.inv_cached && sctx.kk == 9) in_mode = IN_KK9;
+          else in_mode = IN_GENERIC;
+          if (in_mode == IN_KK1 || in_mode == IN_KK9) {
+            for (int j = threadIdx.x; j < sctx.cols; j += kThreads) s_inv[j] = __ldcg(sctx.inv_in + j);
+            if (threadIdx.x == 0) s_inv[sctx.cols] = 1.f;      // IN_KK9 may peek one column past the end
+            __syncthreads();
           }
+          if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0)
+            reset_cols(arena, L[cur_li], R[L[cur_li].rel_in], (sweep & 1) ^ 1);
         }
+        const RowCtx& c = sctx;
+        if (d.kind == TK_DIRECT) {
+          for (int r = 0; r < d.nrows; ++r) cle_row_generic(c, P, d.row0 + r, red, parity, dacc);
+        } else {
+          cle_tile_smem(c, P, in_mode, pipe.stage[sidx], d.row0, d.nrows, s_inv, red, parity, dacc);
+        }
+        bool more = false;
+        if (threadIdx.x == 0) {
+          more = ahead.valid();
+          if (more) { ahead.fill(nd, arena); ahead.next(); }
+        }
+        pipe.release<true>(sidx, more, nd);
+        it.next();
       }
+      pipe.drain();
       flush();
       grid.sync();
+      mark();
       if (step_rescan[p]) {   // general middle layers of this step: round-robin over their scan tiles
         long long sbase = 0;
         for (int q = step_ptr[p]; q < step_ptr[p + 1]; ++q) {
@@ -525,6 +613,12 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
                            const int32_t* step_layers, int32_t n_steps, const DfqCleParams* params,
                            DfqCleResult* result, int32_t n_groups, int32_t* group_sweeps, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool trace = getenv("DFQ_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+  const auto h0 = now();
+  double h_valid = 0, h_occ = 0, h_upload = 0, h_launch = 0;
   DFQ_REQUIRE(arena && layers && rels && step_ptr && step_layers && params && result, "null argument");
   DFQ_REQUIRE(n_layers > 0 && n_rels > 0 && n_steps > 0 && n_groups > 0, "empty problem");
   memset(result, 0, sizeof(*result));
@@ -574,15 +668,19 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     max_tiles = std::max(max_tiles, t);
   }
 
+  h_valid = ms_since(h0);
   int dev = 0, sms = 0, per_sm = 0, coop = 0;
   DFQ_CUDA(cudaGetDevice(&dev));
   DFQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DFQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) { set_error("device does not support cooperative launch"); return DFQ_E_NOT_COOPERATIVE; }
-  DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cle_engine, kThreads, 0));
+  const size_t dyn_smem = RowPipe::smem_bytes();
+  DFQ_CUDA(cudaFuncSetAttribute(k_cle_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+  DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cle_engine, kThreads, dyn_smem));
   if (per_sm < 1) { set_error("persistent kernel does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
   const int grid = (int)std::min<int64_t>((int64_t)sms * per_sm, max_tiles);
 
+  h_occ = ms_since(h0);
   const int n_entries = step_ptr[n_steps];
   std::vector<long long> pass_ptr(n_entries + 1, 0);
   for (int q = 0; q < n_entries; ++q) pass_ptr[q + 1] = pass_ptr[q] + pass_tiles(layers[step_layers[q]]);
@@ -594,34 +692,33 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
       scan_ptr.push_back(scan_ptr.back() + scan_tiles(rels[layers[i].rel_in].groups, rels[layers[i].rel_in].go));
     }
   int n_scan = (int)scan_layers.size();
-  long long *dPP = nullptr, *dSCP = nullptr; int32_t* dSCL = nullptr;
-  DfqLayer* dL = nullptr; DfqRelation* dR = nullptr; int32_t *dSP = nullptr, *dSL = nullptr, *dRS = nullptr;
+  TablePack tp;
+  const int iL = tp.add(layers, n_layers), iR = tp.add(rels, n_rels), iSP = tp.add(step_ptr, n_steps + 1);
+  const int iSL = tp.add(step_layers, n_entries), iRS = tp.add(rescan.data(), n_steps);
+  const int iPP = tp.add(pass_ptr.data(), n_entries + 1), iSCP = tp.add(scan_ptr.data(), n_scan + 1);
+  const int iSCL = tp.add(scan_layers.data(), n_scan);
+  int rc;
+  if ((rc = tp.upload(st))) return rc;
+  DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqRelation* dR = tp.ptr<DfqRelation>(iR);
+  int32_t *dSP = tp.ptr<int32_t>(iSP), *dSL = tp.ptr<int32_t>(iSL), *dRS = tp.ptr<int32_t>(iRS), *dSCL = tp.ptr<int32_t>(iSCL);
+  long long *dPP = tp.ptr<long long>(iPP), *dSCP = tp.ptr<long long>(iSCP);
   CleCtl* dctl = nullptr;
   GroupState* dG = nullptr;
-  int rc;
-  if ((rc = upload(layers, n_layers, &dL, st))) return rc;
-  if ((rc = upload(rels, n_rels, &dR, st))) return rc;
-  if ((rc = upload(step_ptr, n_steps + 1, &dSP, st))) return rc;
-  if ((rc = upload(step_layers, step_ptr[n_steps], &dSL, st))) return rc;
-  if ((rc = upload(rescan.data(), n_steps, &dRS, st))) return rc;
-  if ((rc = upload(pass_ptr.data(), n_entries + 1, &dPP, st))) return rc;
-  if ((rc = upload(scan_ptr.data(), n_scan + 1, &dSCP, st))) return rc;
-  if ((rc = upload(scan_layers.data(), n_scan, &dSCL, st))) return rc;
   DFQ_CUDA(cudaMallocAsync((void**)&dctl, sizeof(CleCtl), st));
   DFQ_CUDA(cudaMemsetAsync(dctl, 0, sizeof(CleCtl), st));
   DFQ_CUDA(cudaMallocAsync((void**)&dG, sizeof(GroupState) * n_groups, st));
   DFQ_CUDA(cudaMemsetAsync(dG, 0, sizeof(GroupState) * n_groups, st));
-
+  h_upload = ms_since(h0);
   DfqCleParams P = *params;
   void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS,
                   &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups};
-  DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kThreads), args, 0, st));
+  DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kThreads), args, dyn_smem, st));
+  h_launch = ms_since(h0);
   CleCtl h;
   std::vector<GroupState> hg(n_groups);
   DFQ_CUDA(cudaMemcpyAsync(&h, dctl, sizeof(CleCtl), cudaMemcpyDeviceToHost, st));
   DFQ_CUDA(cudaMemcpyAsync(hg.data(), dG, sizeof(GroupState) * n_groups, cudaMemcpyDeviceToHost, st));
-  free_async(dL, st); free_async(dR, st); free_async(dSP, st); free_async(dSL, st); free_async(dRS, st);
-  free_async(dPP, st); free_async(dSCP, st); free_async(dSCL, st);
+  tp.release(st);
   free_async(dctl, st); free_async(dG, st);
   DFQ_CUDA(cudaStreamSynchronize(st));
   result->n_sweeps = 0;
@@ -630,6 +727,13 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     result->n_sweeps = std::max(result->n_sweeps, hg[g].n_sweeps);
     result->converged &= hg[g].converged;
     if (group_sweeps) group_sweeps[g] = hg[g].n_sweeps;
+  }
+  if (trace) {
+    fprintf(stderr, "[dfq_cle_run] host ms: validate %.3f occupancy %.3f upload %.3f launch %.3f done %.3f\n", h_valid, h_occ,
+            h_upload, h_launch, ms_since(h0));
+    fprintf(stderr, "[dfq_cle_run] grid %d (%d CTAs/SM) sweeps %d; phase ms:", grid, per_sm, result->n_sweeps);
+    for (int i = 1; i < 16 && h.t_ns[i]; ++i) fprintf(stderr, " %.3f", (h.t_ns[i] - h.t_ns[i - 1]) * 1e-6);
+    fprintf(stderr, "\n");
   }
   result->last_diff = hg[0].diff;
   memcpy(result->diffs, h.diffs, sizeof(h.diffs));

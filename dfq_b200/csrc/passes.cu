@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "rowpipe.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -29,52 +30,82 @@ __device__ __forceinline__ int first_tile(long long base) {
 // ------------------------------------------------------------------------------------------------
 // BN fold
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+struct FoldGeo {
+  float* arena; const DfqLayer* L; const DfqFold* F;
+  __device__ __forceinline__ void operator()(int q, float*& base, int& rows, int& row_len) const {
+    const DfqLayer l = L[F[q].layer];
+    base = arena + l.w_off; rows = l.rows; row_len = l.cols * l.kk;
+  }
+};
+
+// One output row: W[o,:] *= gamma/sqrt(var+eps) in place (shared memory or, for rows larger than a stage, global).
+template <int TPR, bool GLOBAL>
+__device__ __forceinline__ void fold_row(float* arena, const DfqLayer& l, const DfqFold& f, float* row, int o, int lane) {
+  const int n = l.cols * l.kk;
+  // layer_transform.py:251: gamma / sqrt(var + eps) formed first, then multiplied in
+  const float gamma = arena[f.gamma_off + o], var = arena[f.var_off + o];
+  const float den = __fsqrt_rn(__fadd_rn(var, f.bn_eps));
+  const float fac = __fdiv_rn(gamma, den);
+  if (!GLOBAL && (n & 3) == 0) {
+    float4* r4 = (float4*)row;
+    for (int i = lane; i < (n >> 2); i += TPR) {
+      float4 v = r4[i];
+      v.x = __fmul_rn(v.x, fac); v.y = __fmul_rn(v.y, fac); v.z = __fmul_rn(v.z, fac); v.w = __fmul_rn(v.w, fac);
+      r4[i] = v;
+    }
+  } else if (GLOBAL) {
+    for (int i = lane; i < n; i += TPR) stg_stream1(row + i, __fmul_rn(ldg_stream1(row + i), fac));
+  } else {
+    for (int i = lane; i < n; i += TPR) row[i] = __fmul_rn(row[i], fac);
+  }
+  if (lane == 0) {
+    // layer_transform.py:260-261: b*f + (beta - (gamma*mean)/sqrt(var+eps))
+    const float beta = arena[f.beta_off + o], mean = arena[f.mean_off + o];
+    const float b = arena[l.bias_off + o];
+    const float shift = __fsub_rn(beta, __fdiv_rn(__fmul_rn(gamma, mean), den));
+    arena[l.bias_off + o] = __fadd_rn(__fmul_rn(b, fac), shift);
+    arena[f.fake_w_off + o] = fabsf(gamma);   // :264
+    arena[f.fake_b_off + o] = beta;           // :265
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, kPipeCtas)
 k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restrict__ F, int nF,
           const long long* __restrict__ tptr) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  RowPipe pipe;
+  pipe.init(pipe_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TileSpan sp = tile_span(tptr, 0, nF);
-  for (int fi = sp.q; fi < nF && tptr[fi] < sp.hi; ++fi) {
-    const long long base = tptr[fi];
-    const DfqFold f = F[fi];
+  MatIter<FoldGeo> it;
+  it.start(tptr, 0, nF, FoldGeo{arena, L, F});
+  MatIter<FoldGeo> ahead = it;
+  TileDesc nd;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd); pipe.issue(nd); ahead.next(); }
+  while (it.valid()) {
+    const int sidx = pipe.acquire();
+    const TileDesc d = pipe.desc[sidx];
+    const DfqFold f = F[d.task];
     const DfqLayer l = L[f.layer];
     const int row_len = l.cols * l.kk;
-    const bool vec = (row_len % 4 == 0) && (l.w_off % 4 == 0);
-    const bool cta_row = row_len > 2048;
-    const int rpt = cta_row ? 1 : kWarps;
-    const int t0 = (int)(max(sp.lo, base) - base), t1 = (int)(min(sp.hi, tptr[fi + 1]) - base);
-    for (int t = t0; t < t1; ++t) {
-      const int o = cta_row ? t : t * kWarps + warp;
-      if (o >= l.rows) continue;
-      const int tid = cta_row ? (int)threadIdx.x : lane;
-      const int tpr = cta_row ? kThreads : 32;
-      // layer_transform.py:251: gamma / sqrt(var + eps) formed first, then multiplied in
-      const float gamma = arena[f.gamma_off + o], var = arena[f.var_off + o];
-      const float den = __fsqrt_rn(__fadd_rn(var, f.bn_eps));
-      const float fac = __fdiv_rn(gamma, den);
-      float* rowp = arena + l.w_off + (size_t)o * row_len;
-      if (vec) {
-        float4* r4 = (float4*)rowp;
-        for (int i = tid; i < (row_len >> 2); i += tpr) {
-          float4 v = ldg_stream(r4 + i);
-          v.x = __fmul_rn(v.x, fac); v.y = __fmul_rn(v.y, fac);
-          v.z = __fmul_rn(v.z, fac); v.w = __fmul_rn(v.w, fac);
-          stg_stream(r4 + i, v);
-        }
-      } else {
-        for (int i = tid; i < row_len; i += tpr) stg_stream1(rowp + i, __fmul_rn(ldg_stream1(rowp + i), fac));
-      }
-      if (tid == 0) {
-        // layer_transform.py:260-261: b*f + (beta - (gamma*mean)/sqrt(var+eps))
-        const float beta = arena[f.beta_off + o], mean = arena[f.mean_off + o];
-        const float b = arena[l.bias_off + o];
-        const float shift = __fsub_rn(beta, __fdiv_rn(__fmul_rn(gamma, mean), den));
-        arena[l.bias_off + o] = __fadd_rn(__fmul_rn(b, fac), shift);
-        arena[f.fake_w_off + o] = fabsf(gamma);   // :264
-        arena[f.fake_b_off + o] = beta;           // :265
-      }
+    if (d.kind == TK_DIRECT) {
+      for (int r = 0; r < d.nrows; ++r)
+        fold_row<kThreads, true>(arena, l, f, d.gptr + (size_t)r * row_len, d.row0 + r, threadIdx.x);
+    } else if (d.nrows == 1) {
+      fold_row<kThreads, false>(arena, l, f, pipe.stage[sidx], d.row0, threadIdx.x);
+    } else {
+      for (int r = warp; r < d.nrows; r += kWarps)
+        fold_row<32, false>(arena, l, f, pipe.stage[sidx] + (size_t)r * row_len, d.row0 + r, lane);
     }
+    bool more = false;
+    if (threadIdx.x == 0) {
+      more = ahead.valid();
+      if (more) { ahead.fill(nd); ahead.next(); }
+    }
+    pipe.release<true>(sidx, more, nd);
+    it.next();
   }
+  pipe.drain();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,33 +232,92 @@ __device__ __forceinline__ float relu_gauss_mean(float g, float b) {
   return e < 0.f ? 0.f : e;      // NaN stays NaN (expect[expect < 0] = 0)
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+struct BcGeo {
+  float* arena; const DfqLayer* L; const DfqBcLayer* B;
+  __device__ __forceinline__ void operator()(int q, float*& base, int& rows, int& row_len) const {
+    const DfqLayer l = L[B[q].layer];
+    base = arena + l.w_off; rows = l.rows; row_len = l.cols * l.kk;
+  }
+};
+
+constexpr int kExpectCache = 2048;
+
+// eps . E[x] of one output row held in shared (or, for rows larger than a stage, global) memory.
+// Returns the row's dot product in every thread of the row's group.
+template <int TPR, bool RAW>
+__device__ __forceinline__ double bc_row(const float* __restrict__ row, int cols, int kk, const float* __restrict__ ex,
+                                         const QuantScalars& q, int lane) {
+  double acc = 0.0;
+  for (int j = lane; j < cols; j += TPR) {
+    const float* p = row + (size_t)j * kk;
+    float E = 0.f;
+    if (RAW) {                     // bias absorption: sum_k W (dfq.py:150-153)
+      for (int k = 0; k < kk; ++k) E = __fadd_rn(E, p[k]);
+    } else if (kk == 9) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { const float w = p[k]; E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w)); }
+    } else {
+      for (int k = 0; k < kk; ++k) { const float w = p[k]; E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w)); }
+    }
+    acc += (double)E * (double)ex[j];
+  }
+  return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(kThreads, kPipeCtas)
 k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __restrict__ B, int nB,
             const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits,
-            const long long* __restrict__ mm_ptr, const long long* __restrict__ row_ptr) {
+            const long long* __restrict__ row_ptr) {
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[2 * kWarps];
   __shared__ double dred[kWarps];
+  __shared__ __align__(16) float s_ex[kExpectCache];
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  RowPipe pipe;
+  pipe.init(pipe_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TileDesc nd;
 
-  // ---- per-tensor min/max of every corrected weight (dfq.py:14 via :218) ------------------------
+  // ---- per-tensor min/max of every corrected weight (dfq.py:14 via :218), streamed through the pipe ----------
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < nB; i += gridDim.x * kThreads) {
     __stcg(arena + B[i].minmax_off, DFQ_INF);
     __stcg(arena + B[i].minmax_off + 1, -DFQ_INF);
   }
   grid.sync();
   {
-    const TileSpan sp = tile_span(mm_ptr, 0, nB);
-    for (int bi = sp.q; bi < nB && mm_ptr[bi] < sp.hi; ++bi) {
-      const long long base = mm_ptr[bi];
-      const long long k0 = max(sp.lo, base) - base, k1 = min(sp.hi, mm_ptr[bi + 1]) - base;
-      if (k1 <= k0) continue;
-      const DfqLayer l = L[B[bi].layer];
-      const int64_t n = (int64_t)l.rows * l.cols * l.kk;
-      float mn = DFQ_INF, mx = -DFQ_INF;
-      for (long long k = k0; k < k1; ++k) tile_minmax(arena + l.w_off, n, k, mn, mx);
-      cta_minmax_atomic(mn, mx, arena + B[bi].minmax_off, red);
+    MatIter<BcGeo> it;
+    it.start(row_ptr, 0, nB, BcGeo{arena, L, B});
+    MatIter<BcGeo> ahead = it;
+    if (threadIdx.x == 0)
+      for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd); pipe.issue(nd); ahead.next(); }
+    int cur = -1;
+    float mn = DFQ_INF, mx = -DFQ_INF;
+    while (it.valid()) {
+      const int sidx = pipe.acquire();
+      const TileDesc d = pipe.desc[sidx];
+      if (d.task != cur) {
+        if (cur >= 0) cta_minmax_atomic(mn, mx, arena + B[cur].minmax_off, red);
+        cur = d.task; mn = DFQ_INF; mx = -DFQ_INF;
+      }
+      if (d.kind == TK_DIRECT) {
+        for (int i = threadIdx.x; i < d.floats; i += kThreads) { const float v = ldg_stream1(d.gptr + i); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+      } else if ((d.floats & 3) == 0) {
+        const float4* b4 = (const float4*)pipe.stage[sidx];
+        for (int i = threadIdx.x; i < (d.floats >> 2); i += kThreads) {
+          const float4 v = b4[i];
+          mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+          mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+      } else {
+        const float* bf = pipe.stage[sidx];
+        for (int i = threadIdx.x; i < d.floats; i += kThreads) { mn = fminf(mn, bf[i]); mx = fmaxf(mx, bf[i]); }
+      }
+      bool more = false;
+      if (threadIdx.x == 0) { more = ahead.valid(); if (more) { ahead.fill(nd); ahead.next(); } }
+      pipe.release<false>(sidx, more, nd);
+      it.next();
     }
+    if (cur >= 0) cta_minmax_atomic(mn, mx, arena + B[cur].minmax_off, red);
   }
   grid.sync();
 
@@ -248,62 +338,68 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
       }
     }
     grid.sync();
-    // ---- eps . E[x] per output row (dfq.py:216-219,281-293) ------------------------------------------
-    const TileSpan sp = tile_span(row_ptr, level_ptr[lev], level_ptr[lev + 1]);
-    for (int bi = sp.q; bi < level_ptr[lev + 1] && row_ptr[bi] < sp.hi; ++bi) {
-      const long long base = row_ptr[bi];
-      const int t0 = (int)(max(sp.lo, base) - base), t1 = (int)(min(sp.hi, row_ptr[bi + 1]) - base);
-      const DfqBcLayer b = B[bi];
-      const DfqLayer l = L[b.layer];
+    // ---- eps . E[x] per output row (dfq.py:216-219,281-293): rows streamed through the pipe, read only ---------
+    MatIter<BcGeo> it;
+    it.start(row_ptr, level_ptr[lev], level_ptr[lev + 1], BcGeo{arena, L, B});
+    MatIter<BcGeo> ahead = it;
+    if (threadIdx.x == 0)
+      for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd); pipe.issue(nd); ahead.next(); }
+    int cur = -1;
+    DfqBcLayer b; DfqLayer l; QuantScalars q; int so = 1, ex_cached = 0;
+    while (it.valid()) {
+      const int sidx = pipe.acquire();
+      const TileDesc d = pipe.desc[sidx];
+      if (d.task != cur) {
+        cur = d.task;
+        b = B[cur]; l = L[b.layer];
+        q = quant_scalars((double)__ldcg(arena + b.minmax_off), (double)__ldcg(arena + b.minmax_off + 1), num_bits, b.signed_mode);
+        so = l.rows / (b.expect_len / l.cols);
+        ex_cached = (b.expect_len <= kExpectCache);
+        __syncthreads();
+        if (ex_cached) {
+          for (int j = threadIdx.x; j < b.expect_len; j += kThreads) s_ex[j] = __ldcg(arena + b.expect_off + j);
+          __syncthreads();
+        }
+      }
       const int row_len = l.cols * l.kk;
-      const bool cta_row = row_len > 2048;
-      if (t1 > t0) {
-        const QuantScalars q = quant_scalars((double)__ldcg(arena + b.minmax_off), (double)__ldcg(arena + b.minmax_off + 1),
-                                             num_bits, b.signed_mode);
-        const int G = b.expect_len / l.cols;
-        const int so = l.rows / G;
-        for (int t = t0; t < t1; ++t) {
-          const int o = cta_row ? t : t * kWarps + warp;
-          const bool live = o < l.rows;
-          double acc = 0.0;
-          if (live) {
-            const float* rowp = arena + l.w_off + (size_t)o * row_len;
-            const float* ex = arena + b.expect_off + (size_t)(o / so) * l.cols;
-            const int tid = cta_row ? (int)threadIdx.x : lane;
-            const int tpr = cta_row ? kThreads : 32;
-            for (int j = tid; j < l.cols; j += tpr) {
-              float E = 0.f;
-              const float* p = rowp + (size_t)j * l.kk;
-              if (b.flags & 1) {          // raw weight sum: bias absorption, dfq.py:150-153
-                for (int k = 0; k < l.kk; ++k) E = __fadd_rn(E, p[k]);
-              } else {
-                for (int k = 0; k < l.kk; ++k) {
-                  const float w = p[k];
-                  E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w));
-                }
-              }
-              acc += (double)E * (double)__ldcg(ex + j);
-            }
-          }
-          acc = warp_sum(acc);
-          if (cta_row) {
-            __syncthreads();
-            if (lane == 0) dred[warp] = acc;
-            __syncthreads();
-            acc = 0.0;
+      const bool raw = (b.flags & 1) != 0;
+      if (d.nrows == 1) {
+        const int o = d.row0;
+        const float* row = (d.kind == TK_DIRECT) ? d.gptr : pipe.stage[sidx];
+        const float* ex = (ex_cached ? s_ex : arena + b.expect_off) + (size_t)(o / so) * l.cols;
+        double acc = raw ? bc_row<kThreads, true>(row, l.cols, l.kk, ex, q, threadIdx.x)
+                         : bc_row<kThreads, false>(row, l.cols, l.kk, ex, q, threadIdx.x);
+        if (lane == 0) dred[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < kWarps; ++i) acc += dred[i];
-          }
-          const bool leader = live && (cta_row ? threadIdx.x == 0 : lane == 0);
-          if (leader) {
-            const float d = (float)acc;
-            __stcg(arena + b.delta_off + o, d);
-            __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), (b.flags & 2) ? d : -d));  // dfq.py:292 / :164
-            if (b.next_bn_b_off >= 0)                                                                // dfq.py:204-206,293
-              __stcg(arena + b.next_bn_b_off + o, __fadd_rn(__ldcg(arena + b.next_bn_b_off + o), -d));
+          for (int i = 0; i < kWarps; ++i) acc += dred[i];
+          const float dl = (float)acc;
+          __stcg(arena + b.delta_off + o, dl);
+          __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), (b.flags & 2) ? dl : -dl));   // dfq.py:292 / :164
+          if (b.next_bn_b_off >= 0)                                                                    // dfq.py:204-206,293
+            __stcg(arena + b.next_bn_b_off + o, __fadd_rn(__ldcg(arena + b.next_bn_b_off + o), -dl));
+        }
+      } else {
+        for (int r = warp; r < d.nrows; r += kWarps) {
+          const int o = d.row0 + r;
+          const float* row = pipe.stage[sidx] + (size_t)r * row_len;
+          const float* ex = (ex_cached ? s_ex : arena + b.expect_off) + (size_t)(o / so) * l.cols;
+          const double acc = raw ? bc_row<32, true>(row, l.cols, l.kk, ex, q, lane) : bc_row<32, false>(row, l.cols, l.kk, ex, q, lane);
+          if (lane == 0) {
+            const float dl = (float)acc;
+            __stcg(arena + b.delta_off + o, dl);
+            __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), (b.flags & 2) ? dl : -dl));
+            if (b.next_bn_b_off >= 0)
+              __stcg(arena + b.next_bn_b_off + o, __fadd_rn(__ldcg(arena + b.next_bn_b_off + o), -dl));
           }
         }
       }
+      bool more = false;
+      if (threadIdx.x == 0) { more = ahead.valid(); if (more) { ahead.fill(nd); ahead.next(); } }
+      pipe.release<false>(sidx, more, nd);
+      it.next();
     }
     grid.sync();
   }
@@ -313,11 +409,11 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
 
 using namespace dfq;
 
-static int pick_grid(const void* kernel, int64_t max_tiles, int* grid) {
+static int pick_grid(const void* kernel, int64_t max_tiles, int* grid, size_t dyn_smem = 0) {
   int dev = 0, sms = 0, per_sm = 0;
   DFQ_CUDA(cudaGetDevice(&dev));
   DFQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+  DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, dyn_smem));
   if (per_sm < 1) { set_error("kernel does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
   *grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * per_sm, max_tiles));
   return 0;
@@ -333,17 +429,18 @@ extern "C" int dfq_bn_fold(float* arena, int64_t arena_floats, const DfqLayer* l
     DFQ_REQUIRE(folds[i].layer >= 0 && folds[i].layer < n_layers, "fold layer index");
     const DfqLayer& l = layers[folds[i].layer];
     DFQ_REQUIRE(l.w_off >= 0 && l.w_off + (int64_t)l.rows * l.cols * l.kk <= arena_floats, "weight outside arena");
-    tptr[i + 1] = tptr[i] + ((l.cols * l.kk > 2048) ? l.rows : (l.rows + kWarps - 1) / kWarps);
+    tptr[i + 1] = tptr[i] + pipe_tiles(l.rows, l.cols * l.kk);
   }
   int grid, rc;
-  if ((rc = pick_grid((const void*)k_bn_fold, tptr[n_folds], &grid))) return rc;
-  DfqLayer* dL; DfqFold* dF; long long* dP;
-  if ((rc = upload(layers, n_layers, &dL, st))) return rc;
-  if ((rc = upload(folds, n_folds, &dF, st))) return rc;
-  if ((rc = upload(tptr.data(), n_folds + 1, &dP, st))) return rc;
-  k_bn_fold<<<grid, kThreads, 0, st>>>(arena, dL, dF, n_folds, dP);
+  const size_t dyn = RowPipe::smem_bytes();
+  DFQ_CUDA(cudaFuncSetAttribute(k_bn_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  if ((rc = pick_grid((const void*)k_bn_fold, tptr[n_folds], &grid, dyn))) return rc;
+  TablePack tp;
+  const int iL = tp.add(layers, n_layers), iF = tp.add(folds, n_folds), iP = tp.add(tptr.data(), n_folds + 1);
+  if ((rc = tp.upload(st))) return rc;
+  k_bn_fold<<<grid, kThreads, dyn, st>>>(arena, tp.ptr<DfqLayer>(iL), tp.ptr<DfqFold>(iF), n_folds, tp.ptr<long long>(iP));
   DFQ_CUDA(cudaGetLastError());
-  free_async(dL, st); free_async(dF, st); free_async(dP, st);
+  tp.release(st);
   return 0;
 }
 
@@ -363,15 +460,16 @@ extern "C" int dfq_quantize_tensors(float* arena, int64_t arena_floats, const Df
   }
   int grid, rc;
   if ((rc = pick_grid((const void*)k_minmax_tasks, tptr[n_tasks], &grid))) return rc;
-  FlatTask* dT; long long* dP;
-  if ((rc = upload(ft.data(), n_tasks, &dT, st))) return rc;
-  if ((rc = upload(tptr.data(), n_tasks + 1, &dP, st))) return rc;
+  TablePack tp;
+  const int iT = tp.add(ft.data(), n_tasks), iP = tp.add(tptr.data(), n_tasks + 1);
+  if ((rc = tp.upload(st))) return rc;
+  FlatTask* dT = tp.ptr<FlatTask>(iT); long long* dP = tp.ptr<long long>(iP);
   k_minmax_init<<<std::min(148, (n_tasks + 255) / 256), 256, 0, st>>>(arena, dT, n_tasks);
   k_minmax_tasks<<<grid, kThreads, 0, st>>>(arena, dT, n_tasks, dP);
   if (div_mode) k_quant_tasks<true><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks, dP);
   else          k_quant_tasks<false><<<grid, kThreads, 0, st>>>(arena, dT, n_tasks, dP);
   DFQ_CUDA(cudaGetLastError());
-  free_async(dT, st); free_async(dP, st);
+  tp.release(st);
   return 0;
 }
 
@@ -382,8 +480,8 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   DFQ_REQUIRE(arena && layers && bc && terms && level_ptr, "null argument");
   if (n_bc <= 0 || n_levels <= 0) return 0;
   DFQ_REQUIRE(level_ptr[0] == 0 && level_ptr[n_levels] == n_bc, "levels must partition the layer list");
-  int64_t max_tiles = 1, mm_tiles = 0;
-  std::vector<long long> mm_ptr(n_bc + 1, 0), row_ptr(n_bc + 1, 0);
+  int64_t max_tiles = 1;
+  std::vector<long long> row_ptr(n_bc + 1, 0);
   for (int i = 0; i < n_bc; ++i) {
     const DfqBcLayer& b = bc[i];
     DFQ_REQUIRE(b.layer >= 0 && b.layer < n_layers, "bc layer index");
@@ -394,30 +492,21 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
     for (int t = b.term_begin; t < b.term_end; ++t)
       DFQ_REQUIRE(terms[t].dst_off >= 0 && terms[t].dst_off + terms[t].n <= b.expect_len, "term outside expectation vector");
     DFQ_REQUIRE(b.expect_off >= 0 && b.expect_off + b.expect_len <= arena_floats, "expect scratch outside arena");
-    mm_tiles += ((int64_t)l.rows * l.cols * l.kk + kChunk - 1) / kChunk;
-    mm_ptr[i + 1] = mm_tiles;
-    row_ptr[i + 1] = row_ptr[i] + ((l.cols * l.kk > 2048) ? l.rows : (l.rows + kWarps - 1) / kWarps);
+    row_ptr[i + 1] = row_ptr[i] + pipe_tiles(l.rows, l.cols * l.kk);
   }
-  max_tiles = std::max(max_tiles, mm_tiles);
-  for (int lev = 0; lev < n_levels; ++lev) {
-    int64_t t = 0;
-    for (int i = level_ptr[lev]; i < level_ptr[lev + 1]; ++i) {
-      const DfqLayer& l = layers[bc[i].layer];
-      t += (l.cols * l.kk > 2048) ? l.rows : (l.rows + kWarps - 1) / kWarps;
-    }
-    max_tiles = std::max(max_tiles, t);
-  }
+  max_tiles = std::max<int64_t>(max_tiles, row_ptr[n_bc]);
   int grid, rc;
-  if ((rc = pick_grid((const void*)k_bc_engine, max_tiles, &grid))) return rc;
-  DfqLayer* dL; DfqBcLayer* dB; DfqExpectTerm* dT; int32_t* dLP; long long *dMP, *dRP;
-  if ((rc = upload(layers, n_layers, &dL, st))) return rc;
-  if ((rc = upload(bc, n_bc, &dB, st))) return rc;
-  if ((rc = upload(terms, n_terms, &dT, st))) return rc;
-  if ((rc = upload(level_ptr, n_levels + 1, &dLP, st))) return rc;
-  if ((rc = upload(mm_ptr.data(), n_bc + 1, &dMP, st))) return rc;
-  if ((rc = upload(row_ptr.data(), n_bc + 1, &dRP, st))) return rc;
-  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dMP, &dRP};
-  DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, 0, st));
-  free_async(dL, st); free_async(dB, st); free_async(dT, st); free_async(dLP, st); free_async(dMP, st); free_async(dRP, st);
+  const size_t dyn = RowPipe::smem_bytes();
+  DFQ_CUDA(cudaFuncSetAttribute(k_bc_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  if ((rc = pick_grid((const void*)k_bc_engine, max_tiles, &grid, dyn))) return rc;
+  TablePack tp;
+  const int iL = tp.add(layers, n_layers), iB = tp.add(bc, n_bc), iT = tp.add(terms, n_terms);
+  const int iLP = tp.add(level_ptr, n_levels + 1), iRP = tp.add(row_ptr.data(), n_bc + 1);
+  if ((rc = tp.upload(st))) return rc;
+  DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqBcLayer* dB = tp.ptr<DfqBcLayer>(iB); DfqExpectTerm* dT = tp.ptr<DfqExpectTerm>(iT);
+  int32_t* dLP = tp.ptr<int32_t>(iLP); long long* dRP = tp.ptr<long long>(iRP);
+  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP};
+  DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, dyn, st));
+  tp.release(st);
   return 0;
 }

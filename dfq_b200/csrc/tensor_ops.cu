@@ -2,7 +2,9 @@
 // library's host-side plumbing.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -25,6 +27,44 @@ int sm_count() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
+}
+
+namespace {
+struct Slot { unsigned char* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+Slot g_slots[4];
+int g_next_slot = 0;
+std::mutex g_slot_mu;
+bool g_pool_tuned = false;
+}  // namespace
+
+int TablePack::upload(cudaStream_t st) {
+  dev = nullptr;
+  if (total == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  if (!g_pool_tuned) {   // keep freed descriptor blocks in the default pool instead of returning them to the OS at every sync
+    int d = 0; cudaMemPool_t pool;
+    if (cudaGetDevice(&d) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_pool_tuned = true;
+  }
+  Slot& sl = g_slots[g_next_slot];
+  g_next_slot = (g_next_slot + 1) % 4;
+  if (sl.used) DFQ_CUDA(cudaEventSynchronize(sl.ev));
+  if (sl.cap < total) {
+    if (sl.host) cudaFreeHost(sl.host);
+    sl.cap = std::max<size_t>(total, 1 << 20);
+    DFQ_CUDA(cudaHostAlloc((void**)&sl.host, sl.cap, cudaHostAllocDefault));
+  }
+  if (!sl.ev) DFQ_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+  for (int i = 0; i < n; ++i)
+    if (items[i].bytes) memcpy(sl.host + items[i].off, items[i].src, items[i].bytes);
+  DFQ_CUDA(cudaMallocAsync((void**)&dev, total, st));
+  DFQ_CUDA(cudaMemcpyAsync(dev, sl.host, total, cudaMemcpyHostToDevice, st));
+  DFQ_CUDA(cudaEventRecord(sl.ev, st));
+  sl.used = true;
+  return 0;
 }
 
 constexpr int kThreads = 256;
@@ -146,7 +186,7 @@ __device__ inline QuantScalars quant_scalars_f32(float mn, float mx, int num_bit
     scale = recip ? __fmul_rn(d, __frcp_rn(q.qmax)) : __fdiv_rn(d, q.qmax);
   }
   if (1e-8f > scale) scale = 1e-8f;
-  q.neg_min = -mn; q.min_v = mn; q.scale = scale; q.inv_scale = __frcp_rn(scale);
+  q.neg_min = -mn; q.min_v = mn; q.scale = scale; q.inv_scale = (float)(1.0 / (double)scale);
   return q;
 }
 
@@ -300,12 +340,13 @@ extern "C" int dfq_minmax(const float* x, int64_t n, float* out2, void* stream) 
   return 0;
 }
 
-extern "C" int dfq_quant_dequant(const float* x, float* y, int64_t n, float min_value, float scale, float qmin,
+extern "C" int dfq_quant_dequant(const float* x, float* y, int64_t n, float min_value, double scale, float qmin,
                                  float qmax, int div_mode, float* codes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DFQ_REQUIRE(x && y && n > 0, "bad argument");
   QuantScalars q;
-  q.neg_min = -min_value; q.min_v = min_value; q.scale = scale; q.inv_scale = 1.0f / scale; q.qmin = qmin; q.qmax = qmax;
+  q.neg_min = -min_value; q.min_v = min_value; q.scale = (float)scale; q.inv_scale = (float)(1.0 / scale);
+  q.qmin = qmin; q.qmax = qmax;
   const int grid = flat_grid(n, 8);
   if (div_mode) k_quant<true, false, false><<<grid, kThreads, 0, st>>>(x, y, n, q, nullptr, nullptr, 0, 0, 0, codes);
   else          k_quant<false, false, false><<<grid, kThreads, 0, st>>>(x, y, n, q, nullptr, nullptr, 0, 0, 0, codes);

@@ -72,7 +72,7 @@ def fake_quant_explicit(x, num_bits, min_value, max_value, symmetric=False, out=
     else:
         yd = torch.empty_like(xd)
     if xd.numel():
-        _lib.check(lib.dfq_quant_dequant(_ptr(xd), _ptr(yd), xd.numel(), C.c_float(mn), C.c_float(scale),
+        _lib.check(lib.dfq_quant_dequant(_ptr(xd), _ptr(yd), xd.numel(), C.c_float(mn), C.c_double(scale),
                                          C.c_float(qmin), C.c_float(qmax), int(div_mode), None, _lib.stream_ptr()),
                    "dfq_quant_dequant")
     if out is not None and yd is not out:

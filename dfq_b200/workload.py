@@ -245,3 +245,57 @@ class DeviceStack:
     @property
     def launches_per_step(self) -> int:
         return 3 + (3 if self.quant_plan is not None else 0)
+
+
+class HostStackCalibrator:
+    """Calibrate a stack that lives in HOST memory, streaming it through the GPU in chunks.
+
+    The host image is the concatenation of per-chunk state images (what ``DeviceStack.state()`` looks like).  Three
+    streams form a pipeline over the chunks: H2D of chunk i+1 (pinned -> arena B), the kernels on chunk i (arena A),
+    D2H of chunk i-1.  PCIe is full duplex, so a step is bound by max(H2D, D2H, compute) per chunk instead of their sum.
+    """
+
+    def __init__(self, device, chunk_blocks: int = 32, channels: int = 512, k: int = 3, quantize: bool = False):
+        from .engine import Session
+        self.device = device
+        self.slots = []
+        for _ in range(2):
+            sess = Session(device)
+            st = DeviceStack(sess, chunk_blocks, channels, k, quantize=quantize)
+            self.slots.append(st)
+        self.chunk_floats = self.slots[0].state_floats
+        self.chunk_layers = 2 * chunk_blocks
+        self.s_in = torch.cuda.Stream(device)
+        self.s_run = torch.cuda.Stream(device)
+        self.s_out = torch.cuda.Stream(device)
+
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor):
+        """host_in/host_out: pinned fp32 tensors of n_chunks * chunk_floats elements."""
+        n = host_in.numel() // self.chunk_floats
+        F = self.chunk_floats
+        loaded = [torch.cuda.Event() for _ in range(n)]
+        computed = [torch.cuda.Event() for _ in range(n)]
+        stored = [torch.cuda.Event() for _ in range(n)]
+        cur = torch.cuda.current_stream(self.device)
+        self.s_in.wait_stream(cur); self.s_run.wait_stream(cur); self.s_out.wait_stream(cur)
+
+        def load(i):
+            with torch.cuda.stream(self.s_in):
+                if i >= 2:
+                    self.s_in.wait_event(stored[i - 2])          # the slot's previous tenant has left
+                self.slots[i % 2].state().copy_(host_in[i * F:(i + 1) * F], non_blocking=True)
+                loaded[i].record(self.s_in)
+
+        load(0)
+        for i in range(n):
+            if i + 1 < n:
+                load(i + 1)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(loaded[i])
+                self.slots[i % 2].run()                           # returns when the equalization result is back
+                computed[i].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(computed[i])
+                host_out[i * F:(i + 1) * F].copy_(self.slots[i % 2].state(), non_blocking=True)
+                stored[i].record(self.s_out)
+        cur.wait_stream(self.s_out)

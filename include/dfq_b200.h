@@ -204,12 +204,13 @@ int dfq_quantize_tensors(float* arena, int64_t arena_floats, const DfqQuantTask*
 /* out2[0] = min(x), out2[1] = max(x)   (dfq.py:14, layer_transform.py:289, quantize.py:195-196) */
 int dfq_minmax(const float* x, int64_t n, float* out2, void* stream);
 
-/* Fake quantization with explicit scalars (quantize.py:70-74):
- *   t = x + neg_min;  t = div_mode ? t * (1.0f/scale) : t / scale;  t = clamp(t, qmin, qmax);
- *   t = rint(t) [-> codes, if non-null];  y = t * scale;  y = y + min_value.
- * Four separately rounded fp32 ops, no FMA contraction.  div_mode 0 = IEEE division (PyTorch CPU),
- * 1 = multiply by reciprocal (PyTorch CUDA eager with a Python-scalar divisor).  y may alias x. */
-int dfq_quant_dequant(const float* x, float* y, int64_t n, float min_value, float scale,
+/* Fake quantization with explicit scalars (quantize.py:70-74); `scale` is the Python double of quantize.py:64-66:
+ *   t = x + (-min);  t = div_mode ? t * fp32(1.0/scale) : t / fp32(scale);  t = clamp(t, qmin, qmax);
+ *   t = rint(t) [-> codes, if non-null];  y = t * fp32(scale);  y = y + min_value.
+ * Four separately rounded fp32 ops, no FMA contraction.  div_mode 0 = IEEE division (PyTorch CPU), 1 = multiply by
+ * the reciprocal formed in double and rounded to fp32 - what PyTorch CUDA eager computes for `div_(python_float)`
+ * [probed on B200, torch 2.11].  y may alias x. */
+int dfq_quant_dequant(const float* x, float* y, int64_t n, float min_value, double scale,
                       float qmin, float qmax, int div_mode, float* codes, void* stream);
 
 /* Same with the range taken from device memory (*min_ptr, *max_ptr: e.g. the two halves of a dfq_minmax

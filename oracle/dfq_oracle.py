@@ -66,7 +66,8 @@ def quantize(x: np.ndarray, num_bits: int = 8, min_value: Optional[float] = None
     rounded fp32 ops around a clamp and a round-half-even.
 
     div_mode "div"   : true IEEE division  (PyTorch CPU, ``div_(python_float)``)
-    div_mode "recip" : ``t * (1.0f / scale)``  (PyTorch CUDA eager with a Python-scalar divisor)
+    div_mode "recip" : ``t * fp32(1.0 / scale)`` with the reciprocal formed in double from the Python scalar - what PyTorch
+                       CUDA eager computes for ``div_(python_float)`` [probed on B200 with torch 2.11]
     """
     x = np.ascontiguousarray(x, dtype=f32)
     if min_value is None:
@@ -79,7 +80,7 @@ def quantize(x: np.ndarray, num_bits: int = 8, min_value: Optional[float] = None
     if div_mode == "div":
         t = t / s32
     elif div_mode == "recip":
-        t = t * (f32(1.0) / s32)
+        t = t * f32(1.0 / scale)
     else:
         raise ValueError(div_mode)
     t = np.minimum(np.maximum(t, f32(qmin)), f32(qmax))

@@ -193,9 +193,10 @@ class FakeLib:
 
     def dfq_quant_dequant(self, x_p, y_p, n, mn, scale, qmin, qmax, div_mode, codes_p, stream):
         x = _floats(x_p, n); y = _floats(y_p, n)
+        scale_d = float(_val(scale))
         mn, scale, qmin, qmax = (f32(_val(v)) for v in (mn, scale, qmin, qmax))
         t = x + (-mn)
-        t = t * (f32(1) / scale) if div_mode else t / scale
+        t = t * f32(1.0 / scale_d) if div_mode else t / scale
         t = np.rint(np.minimum(np.maximum(t, qmin), qmax))
         y[...] = t * scale + mn
         return 0

@@ -184,3 +184,36 @@ def test_quantize_function_and_observer_follow_reference_fixture(monkeypatch):
     conv = Q.QuantNConv2d(3, 4, 3)
     Q.set_layer_bits({1: conv}, 6, 6, 16, [Q.QuantNConv2d])
     assert conv.quant.update_stat == 6 and conv.quant.num_bits == 8
+
+
+def test_graph_calibration_equals_the_four_separate_calls(monkeypatch):
+    """dfq_b200.calibrate.GraphCalibration (one staging, fused plan) == merge_batchnorm + create_relation +
+    cross_layer_equalization + bias_correction + quantize_targ_layer called one after the other."""
+    fakelib.install(monkeypatch)
+    from dfq_b200 import dfq
+    from dfq_b200.calibrate import GraphCalibration
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    topo = workload.load_topology(os.path.join(GOLD, "topology_resnet18.json"))
+    targ = [nn.Conv2d, nn.Linear]
+    ga, ba, _ = workload.build_graph(topo, seed=11)
+    gb, bb, _ = workload.build_graph(topo, seed=11)
+    LT.merge_batchnorm(None, ga, ba, targ)
+    rels = create_relation(ga, ba, targ)
+    dfq.cross_layer_equalization(ga, rels, targ)
+    dfq.bias_correction(ga, ba, targ)
+    LT.quantize_targ_layer(ga, 8, 16, targ)
+    cal = GraphCalibration(gb, bb, targ)
+    res = cal.run(equalize=True, correction=True, quantize_bits=(8, 16))
+    assert res.n_sweeps == dfq.cross_layer_equalization.last_result.n_sweeps
+    assert len(cal.relations) == len(rels)
+    for ra, rb in zip(rels, cal.relations):
+        assert np.array_equal(ra.S.numpy(), rb.S.numpy())
+    for (ka, ma), (kb, mb) in zip(ga.items(), gb.items()):
+        if type(ma) in targ:
+            assert np.array_equal(ma.weight.detach().numpy(), mb.weight.detach().numpy())
+            assert np.array_equal(ma.bias.detach().numpy(), mb.bias.detach().numpy())
+        if isinstance(ma, nn.BatchNorm2d) and hasattr(ma, "fake_bias"):
+            assert np.array_equal(ma.fake_bias.numpy(), mb.fake_bias.numpy())
+            assert np.array_equal(ma.fake_weight.numpy(), mb.fake_weight.numpy())
+            assert float(mb.weight.min()) == 1.0 and float(mb.running_var.max()) == 1.0 and mb.eps in (0, 1e-12)
