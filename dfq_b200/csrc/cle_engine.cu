@@ -35,8 +35,13 @@ namespace cg = cooperative_groups;
 
 namespace dfq {
 
-constexpr int kThreads = 256;
+// CTA = 7 consumer warps (the arithmetic) + 1 producer warp (TMA loads/stores and the per-row scalar bookkeeping),
+// see "warp-specialised pass" below.  kThreads / kWarps count the CONSUMERS: every tile loop and reduction strides by them.
+constexpr int kThreads = 224;
 constexpr int kWarps = kThreads / 32;
+constexpr int kCtaThreads = kThreads + 32;
+// barrier among the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 constexpr int kScanRows = 32;      // rows per column-scan tile
 constexpr int kScanCols = 2048;    // columns kept in shared memory by a scan tile
 #ifndef DFQ_INV_CACHE
@@ -124,52 +129,54 @@ __device__ __forceinline__ void cta_minmax(float& mn, float& mx, float* red, int
   float* r = red + (parity & 1) * 2 * kWarps;
   parity++;
   if (l == 0) { r[w] = mn; r[kWarps + w] = mx; }
-  __syncthreads();
-  float a = r[l & (kWarps - 1)], b = r[kWarps + (l & (kWarps - 1))];
+  cbar();
+  float a = r[0], b = r[kWarps];
 #pragma unroll
-  for (int o = kWarps / 2; o > 0; o >>= 1) {
-    a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-  }
+  for (int i = 1; i < kWarps; ++i) { a = fminf(a, r[i]); b = fmaxf(b, r[kWarps + i]); }
   mn = a; mx = b;
 }
 
+// Per-stage mailbox between the producer warp and the consumers for single-row tiles:
+//   producer -> consumers : cmn/cmx, the column extrema of the second layer for this channel (prefetched with the tile)
+//   consumers -> producer : s / inv of this sweep; the producer then does the per-channel bookkeeping (publish_row)
+struct StagePub { float cmn, cmx, s, inv; int valid; int pad[3]; };
+
+// The per-channel bookkeeping of dfq.py:62-70 + relation.py:20-24 + the derived column extrema, for ONE channel.
+__device__ __forceinline__ void publish_row(const RowCtx& c, const DfqCleParams& P, int o, float s, float inv, float cmn, float cmx) {
+  c.s_step[o] = s;
+  __stcg(c.inv_out + o, inv);
+  if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(__ldcg(c.s_acc + o), s);
+  __stcg(c.bias + o, __fmul_rn(__ldcg(c.bias + o), s));
+  if (c.bnw) __stcg(c.bnw + o, __fmul_rn(__ldcg(c.bnw + o), s));
+  if (c.bnb) __stcg(c.bnb + o, __fmul_rn(__ldcg(c.bnb + o), s));
+  if (c.cmin_wr) {  // derived column extrema of the second layer after its column scaling
+    __stcg(c.cmin_wr + o, __fmul_rn(cmn, inv));
+    __stcg(c.cmax_wr + o, __fmul_rn(cmx, inv));
+  }
+  if (c.own_cmin_wr) {  // depthwise middle layer: its single-row column is this row
+    __stcg(c.own_cmin_wr + o, __fmul_rn(__ldcg(c.own_cmin_wr + o), s));
+    __stcg(c.own_cmax_wr + o, __fmul_rn(__ldcg(c.own_cmax_wr + o), s));
+  }
+}
+
 // All threads of the row's group call this with the reduced row extrema; the leader publishes.
+__device__ __forceinline__ float solve_only(const RowCtx& c, const DfqCleParams& P, int o, float mn, float mx, float cmn,
+                                            float cmx, float* inv) {
+  if (P.apply_only) {          // replay a given scale vector (multi-GPU replicas): s = S[o], columns get 1/S[o]
+    const float s = __ldcg(c.s_acc + o);
+    *inv = __frcp_rn(s);
+    return s;
+  }
+  return solve_scale(range_of(mn, mx, P.signed_mode), range_of(cmn, cmx, P.signed_mode), P, inv);
+}
 __device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCleParams& P, int o,
                                                    float mn, float mx, float cmn, float cmx, bool leader) {
-  const float r1 = range_of(mn, mx, P.signed_mode);
-  const float r2 = range_of(cmn, cmx, P.signed_mode);
   float inv;
-  float s;
-  if (P.apply_only) {          // replay a given scale vector (multi-GPU replicas): s = S[o], columns get 1/S[o]
-    s = __ldcg(c.s_acc + o);
-    inv = __frcp_rn(s);
-  } else {
-    s = solve_scale(r1, r2, P, &inv);
-  }
-  if (leader) {
-    c.s_step[o] = s;
-    __stcg(c.inv_out + o, inv);
-    if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(c.s_acc[o], s);
-    c.bias[o] = __fmul_rn(c.bias[o], s);
-    if (c.bnw) c.bnw[o] = __fmul_rn(c.bnw[o], s);
-    if (c.bnb) c.bnb[o] = __fmul_rn(c.bnb[o], s);
-    if (c.cmin_wr) {  // derived column extrema of the second layer after its column scaling
-      __stcg(c.cmin_wr + o, __fmul_rn(cmn, inv));
-      __stcg(c.cmax_wr + o, __fmul_rn(cmx, inv));
-    }
-    if (c.own_cmin_wr) {  // depthwise middle layer: its single-row column is this row
-      __stcg(c.own_cmin_wr + o, __fmul_rn(__ldcg(c.own_cmin_wr + o), s));
-      __stcg(c.own_cmax_wr + o, __fmul_rn(__ldcg(c.own_cmax_wr + o), s));
-    }
-  }
+  const float s = solve_only(c, P, o, mn, mx, cmn, cmx, &inv);
+  if (leader) publish_row(c, P, o, s, inv, cmn, cmx);
   return s;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// One tile (nrows consecutive rows of one layer) resident in shared memory: range reduction, s, rescale IN PLACE.
-// TPR = threads per row: kThreads (the whole CTA on one long row, block reduction) or 32 (one warp per row).
-// ------------------------------------------------------------------------------------------------------------
 // How the reciprocal scales of the in-relation map onto the elements of a row (decided once per layer):
 enum InMode { IN_NONE = 0, IN_UNIFORM, IN_KK1, IN_KK9, IN_GENERIC };
 
@@ -211,7 +218,8 @@ __device__ __forceinline__ float in_scale1(float t, int e, const float* __restri
 // which would force the compiler to reload it after every store.
 template <int TPR, int MODE, bool HAS_OUT>
 __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams& P, float* __restrict__ row, int o, int lane,
-                                             const float* __restrict__ s_inv, float* red, int& parity, double& dacc) {
+                                             const float* __restrict__ s_inv, float* red, int& parity, double& dacc,
+                                             StagePub* pub = nullptr) {
   const int n = c.row_len, kk = c.kk;
   const bool vec = ((n & 3) == 0);
   const double inv_n = c.inv_n;
@@ -222,7 +230,9 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
   else if (MODE == IN_GENERIC) inv = c.inv_in + (o / c.in_go) * c.in_gi;
   float s = 1.f;
   if (HAS_OUT) {
-    const float cmn = __ldcg(c.cmin_rd + o), cmx = __ldcg(c.cmax_rd + o);   // in flight during the reduction
+    float cmn, cmx;
+    if (pub) { cmn = pub->cmn; cmx = pub->cmx; }                             // prefetched by the producer warp
+    else { cmn = __ldcg(c.cmin_rd + o); cmx = __ldcg(c.cmax_rd + o); }       // in flight during the reduction
     float mn = DFQ_INF, mx = -DFQ_INF;
     if (vec) {
       const float4* r4 = (const float4*)row;
@@ -241,7 +251,13 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
     }
     if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
     else cta_minmax(mn, mx, red, parity);
-    s = solve_and_publish(c, P, o, mn, mx, cmn, cmx, lane == 0);
+    if (pub) {      // the producer warp does the bookkeeping after the tile is handed back
+      float inv;
+      s = solve_only(c, P, o, mn, mx, cmn, cmx, &inv);
+      if (lane == 0) { pub->s = s; pub->inv = inv; }
+    } else {
+      s = solve_and_publish(c, P, o, mn, mx, cmn, cmx, lane == 0);
+    }
   }
   float dsum = 0.f;
   if (vec) {
@@ -269,10 +285,10 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
 
 template <int MODE, bool HAS_OUT>
 __device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams& P, float* buf, int row0, int nrows,
-                                              const float* s_inv, float* red, int& parity, double& dacc) {
+                                              const float* s_inv, float* red, int& parity, double& dacc, StagePub* pub) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (nrows == 1) {
-    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, row0, threadIdx.x, s_inv, red, parity, dacc);
+    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, row0, threadIdx.x, s_inv, red, parity, dacc, HAS_OUT ? pub : nullptr);
   } else {
     const int row_len = c.row_len;
     for (int r = warp; r < nrows; r += kWarps)
@@ -281,12 +297,13 @@ __device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParam
 }
 
 __device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParams& P, int in_mode, float* buf, int row0,
-                                              int nrows, const float* s_inv, float* red, int& parity, double& dacc) {
-#define DFQ_TILE(M)                                                                              \
-  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc);       \
-  else cle_tile_rows<M, false>(c, P, buf, row0, nrows, s_inv, red, parity, dacc);
+                                              int nrows, const float* s_inv, float* red, int& parity, double& dacc,
+                                              StagePub* pub) {
+#define DFQ_TILE(M)                                                                                   \
+  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub);       \
+  else cle_tile_rows<M, false>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub);
   switch (in_mode) {
-    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc); break;
+    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub); break;
     case IN_UNIFORM: DFQ_TILE(IN_UNIFORM) break;
     case IN_KK1: DFQ_TILE(IN_KK1) break;
     case IN_KK9: DFQ_TILE(IN_KK9) break;
@@ -371,7 +388,7 @@ __device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int
   const bool use_smem = (J <= kScanCols);
   if (use_smem) {
     for (int j = threadIdx.x; j < J; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
-    __syncthreads();
+    cbar();
   }
   for (int p = threadIdx.x; p < row_len; p += kThreads) {
     float mn = DFQ_INF, mx = -DFQ_INF;
@@ -386,12 +403,12 @@ __device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int
     else { atomic_min_f(dmin + g * gi + j, mn); atomic_max_f(dmax + g * gi + j, mx); }
   }
   if (use_smem) {
-    __syncthreads();
+    cbar();
     for (int j = threadIdx.x; j < J; j += kThreads) {
       atomic_min_f(dmin + g * gi + j, smin[j]);
       atomic_max_f(dmax + g * gi + j, smax[j]);
     }
-    __syncthreads();
+    cbar();
   }
 }
 
@@ -457,36 +474,146 @@ struct PassIter {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, kPipeCtas)
+// ------------------------------------------------------------------------------------------------------------
+// Warp-specialised pass.  Shared-memory ring of kPipeStages tiles per CTA:
+//   producer warp (lane 0):  for every tile  [expect_tx + cp.async.bulk load] -> prefetch the channel's column extrema into the
+//                            stage mailbox -> arrive(full);  when the consumers hand a tile back (done):  per-channel bookkeeping
+//                            (S, 1/s, bias, BN vectors, derived column extrema) -> cp.async.bulk store -> stage free
+//   consumer warps (7):      wait(full) -> range reduction -> s -> rescale in place -> fence.proxy.async -> arrive(done)
+// The consumers never wait for global-memory latency of the small vectors nor for the TMA bookkeeping, and the producer is
+// off their critical path: ONE consumer barrier per tile (the block reduction).
+// ------------------------------------------------------------------------------------------------------------
+struct WsPipe {
+  float* stage[kPipeStages];
+  uint64_t* full;     // [S] producer -> consumers (1 arrival + tx bytes)
+  uint64_t* done;     // [S] consumers -> producer (kThreads arrivals)
+  TileDesc* desc;     // [S]
+  StagePub* pub;      // [S]
+  __device__ void init(unsigned char* smem) {
+    for (int i = 0; i < kPipeStages; ++i) stage[i] = (float*)(smem + (size_t)i * kStageBytes);
+    unsigned char* p = smem + (size_t)kPipeStages * kStageBytes;
+    full = (uint64_t*)p;
+    done = (uint64_t*)(p + 64);
+    desc = (TileDesc*)(p + 128);
+    pub = (StagePub*)(p + 128 + kPipeStages * sizeof(TileDesc));
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kPipeStages; ++i) { mbar_init(full + i, 1); mbar_init(done + i, kThreads); }
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  static constexpr size_t smem_bytes() {
+    return (size_t)kPipeStages * kStageBytes + 128 + kPipeStages * (sizeof(TileDesc) + sizeof(StagePub)) + 64;
+  }
+};
+static_assert(kPipeStages <= 8, "barrier arrays are 64 bytes");
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Producer WARP: issue / retire the tiles of one step.  `count` = tiles this CTA has moved since kernel start.
+// One iteration retires tile m (consumers are done with it) and issues tile m + kPipeStages into the stage it frees;
+// three lanes work side by side so the iteration costs ONE global-memory latency instead of their sum:
+//   lane 0  bulk store of tile m -> wait until the store has read the stage -> bulk load of the new tile
+//   lane 1  per-channel bookkeeping of tile m (publish_row: S, 1/s, bias, BN vectors, derived column extrema)
+//   lane 2  prefetch of the new tile's column extrema into its mailbox
+__device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
+                           unsigned long long& count, const DfqCleParams& P, int sweep) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long n = count, m = count;     // next tile to issue / to retire (uniform across the warp)
+  RowCtx ctx;                                  // lane 1: layer being retired; lane 2: layer being issued
+  int li = -1;
+  for (;;) {
+    const bool room = (n - m) < (unsigned long long)kPipeStages;
+    if (!(pit.valid() && room) && m == n) break;
+    const bool do_retire = !room || !pit.valid();
+    if (do_retire) {
+      const int sr = (int)(m % kPipeStages);
+      mbar_wait(ws.done + sr, (uint32_t)((m / kPipeStages) & 1));          // the consumers are done with tile m
+      const TileDesc d = ws.desc[sr];
+      const StagePub pb = ws.pub[sr];
+      __syncwarp();                                                          // everyone holds a copy before the stage is recycled
+      if (lane == 0 && d.kind == TK_BULK) {
+        bulk_s2g(d.gptr, ws.stage[sr], (uint32_t)d.floats * 4u);
+        bulk_commit();
+        bulk_wait_read<0>();                                                 // the stage may be overwritten now
+      }
+      if (lane == 1 && pb.valid) {
+        if (d.task != li) { make_ctx(ctx, arena, L, R, d.task, sweep); li = d.task; }
+        publish_row(ctx, P, d.row0, pb.s, pb.inv, pb.cmn, pb.cmx);
+      }
+      m++;
+    }
+    if (pit.valid() && (n - m) < (unsigned long long)kPipeStages) {
+      TileDesc d;
+      pit.fill(d, arena);
+      pit.next();
+      const int si = (int)(n % kPipeStages);
+      if (lane == 0) {
+        ws.desc[si] = d;
+        if (d.kind == TK_BULK) {
+          mbar_expect_tx(ws.full + si, (uint32_t)d.floats * 4u);
+          bulk_g2s(ws.stage[si], d.gptr, (uint32_t)d.floats * 4u, ws.full + si);
+        }
+      }
+      if (lane == 2) {
+        StagePub pb; pb.valid = 0; pb.cmn = pb.cmx = pb.s = pb.inv = 0.f;
+        if (d.nrows == 1 && d.kind != TK_DIRECT) {
+          if (d.task != li) { make_ctx(ctx, arena, L, R, d.task, sweep); li = d.task; }
+          if (ctx.has_out) { pb.cmn = __ldcg(ctx.cmin_rd + d.row0); pb.cmx = __ldcg(ctx.cmax_rd + d.row0); pb.valid = 1; }
+        }
+        ws.pub[si] = pb;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ws.full + si);   // phase completes when this arrival AND the bulk bytes have landed
+      n++;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    bulk_wait_all();
+    fence_proxy_async_all();
+    __threadfence();
+  }
+  __syncwarp();
+  count = n;
+}
+
+__global__ void __launch_bounds__(kCtaThreads, kPipeCtas)
 k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelation* __restrict__ R, int nR,
              const int* __restrict__ step_ptr, const int* __restrict__ step_layers, int n_steps,
              const int* __restrict__ step_rescan, const long long* __restrict__ pass_ptr,
              const long long* __restrict__ scan_ptr, const int* __restrict__ scan_layers, int n_scan,
              DfqCleParams P, CleCtl* ctl, GroupState* G, int nG) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ float red[2 * 2 * kWarps];
-  __shared__ __align__(16) float s_inv[kInvCache + 4];   // 1/s of the current layer's input columns
-  __shared__ double dred[kWarps];
+  __shared__ float red[2 * 2 * 8];
+  __shared__ double dred[8];
   __shared__ RowCtx sctx;
+  __shared__ __align__(16) float s_inv[kInvCache + 4];   // 1/s of the current layer's input columns
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   // the column-scan scratch aliases the (idle) first pipe stage: scans and passes never overlap
   float* smin = (float*)pipe_smem;
   float* smax = smin + kScanCols;
   static_assert(2 * kScanCols * sizeof(float) <= (size_t)kStageBytes, "scan scratch must fit one stage");
-  RowPipe pipe;
-  pipe.init(pipe_smem);
+  WsPipe ws;
+  ws.init(pipe_smem);
+  const bool producer = threadIdx.x >= kThreads;
   int parity = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long count = 0;     // tiles moved through the ring so far (advances identically in both roles)
 
   int tmark = 0;
   auto mark = [&]() { if (blockIdx.x == 0 && threadIdx.x == 0 && tmark < 16) ctl->t_ns[tmark] = gtimer(); tmark++; };
   mark();
   // ---- phase 0: column extrema of every `second` layer (buffer 0) -----------------------------
-  for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) G[g].diff = 10.0;   // dfq.py:81
-  for (int li = blockIdx.x; li < nL; li += gridDim.x)
-    if (L[li].rel_in >= 0) reset_cols(arena, L[li], R[L[li].rel_in], 0);
+  if (!producer) {
+    for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) G[g].diff = 10.0;   // dfq.py:81
+    for (int li = blockIdx.x; li < nL; li += gridDim.x)
+      if (L[li].rel_in >= 0) reset_cols(arena, L[li], R[L[li].rel_in], 0);
+  }
   grid.sync();
-  {  // scan_ptr[0 .. n_scan]: tile prefix over scan_layers (all `second` layers)
+  if (!producer) {  // scan_ptr[0 .. n_scan]: tile prefix over scan_layers (all `second` layers)
     const TileSpan sp = tile_span(scan_ptr, 0, n_scan);
     for (int q = sp.q; q < n_scan && scan_ptr[q] < sp.hi; ++q) {
       const long long base = scan_ptr[q];
@@ -499,83 +626,93 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
   for (int sweep = 0;; ++sweep) {
     const int slot = sweep % 3;
     for (int p = 0; p < n_steps; ++p) {
-      double dacc = 0.0;
-      int cur_g = -1;
-      // sum the CTA's partial of group cur_g into that group's accumulator (one atomic)
-      auto flush = [&]() {
-        if (cur_g < 0) return;
-        dacc = warp_sum(dacc);
-        __syncthreads();
-        if (lane == 0) dred[warp] = dacc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          double t = 0.0;
-#pragma unroll
-          for (int i = 0; i < kWarps; ++i) t += dred[i];
-          if (t != 0.0) atomicAdd(&G[cur_g].acc[slot], t);
-        }
-        dacc = 0.0;
-      };
       PassIter it;
       it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
-      PassIter ahead = it;
-      TileDesc nd;
-      if (threadIdx.x == 0)
-        for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd, arena); pipe.issue(nd); ahead.next(); }
-      int cur_li = -1, in_mode = IN_NONE;
-      while (it.valid()) {
-        const int sidx = pipe.acquire();
-        const TileDesc d = pipe.desc[sidx];
-        if (d.task != cur_li) {
-          cur_li = d.task;
-          const int g = L[cur_li].group;
-          if (g != cur_g) { flush(); cur_g = g; }
-          __syncthreads();                       // everyone is done with the previous layer's context
-          if (threadIdx.x == 0) make_ctx(sctx, arena, L, R, cur_li, sweep);
-          __syncthreads();
-          if (sctx.inv_in == nullptr) in_mode = IN_NONE;
-          else if (sctx.cols == 1) in_mode = IN_UNIFORM;
-          else if (sctx.inv_cached && sctx.kk == 1) in_mode = IN_KK1;
-          else if (sctx.inv_cached && sctx.kk == 9) in_mode = IN_KK9;
-          else in_mode = IN_GENERIC;
-          if (in_mode == IN_KK1 || in_mode == IN_KK9) {
-            for (int j = threadIdx.x; j < sctx.cols; j += kThreads) s_inv[j] = __ldcg(sctx.inv_in + j);
-            if (threadIdx.x == 0) s_inv[sctx.cols] = 1.f;      // IN_KK9 may peek one column past the end
-            __syncthreads();
+      if (producer) {
+        ws_produce(arena, L, R, it, ws, count, P, sweep);
+      } else {
+        double dacc = 0.0;
+        int cur_g = -1;
+        // sum the CTA's partial of group cur_g into that group's accumulator (one atomic)
+        auto flush = [&]() {
+          if (cur_g < 0) return;
+          dacc = warp_sum(dacc);
+          cbar();
+          if (lane == 0) dred[warp] = dacc;
+          cbar();
+          if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kWarps; ++i) t += dred[i];
+            if (t != 0.0) atomicAdd(&G[cur_g].acc[slot], t);
           }
-          if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0)
-            reset_cols(arena, L[cur_li], R[L[cur_li].rel_in], (sweep & 1) ^ 1);
+          dacc = 0.0;
+        };
+        int cur_li = -1, in_mode = IN_NONE;
+        while (it.valid()) {
+          const int sidx = (int)(count % kPipeStages);
+          mbar_wait(ws.full + sidx, (uint32_t)((count / kPipeStages) & 1));
+          const TileDesc d = ws.desc[sidx];
+          float* buf = ws.stage[sidx];
+          if (d.kind == TK_PLAIN) {            // a tile the TMA unit cannot move: cooperative fetch
+            for (int i = threadIdx.x; i < d.floats; i += kThreads) buf[i] = ldg_stream1(d.gptr + i);
+            cbar();
+          }
+          if (d.task != cur_li) {
+            cur_li = d.task;
+            const int g = L[cur_li].group;
+            if (g != cur_g) { flush(); cur_g = g; }
+            cbar();                              // everyone is done with the previous layer's context
+            if (threadIdx.x == 0) make_ctx(sctx, arena, L, R, cur_li, sweep);
+            cbar();
+            if (sctx.inv_in == nullptr) in_mode = IN_NONE;
+            else if (sctx.cols == 1) in_mode = IN_UNIFORM;
+            else if (sctx.inv_cached && sctx.kk == 1) in_mode = IN_KK1;
+            else if (sctx.inv_cached && sctx.kk == 9) in_mode = IN_KK9;
+            else in_mode = IN_GENERIC;
+            if (in_mode == IN_KK1 || in_mode == IN_KK9) {
+              for (int j = threadIdx.x; j < sctx.cols; j += kThreads) s_inv[j] = __ldcg(sctx.inv_in + j);
+              if (threadIdx.x == 0) s_inv[sctx.cols] = 1.f;
+              cbar();
+            }
+            if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0)
+              reset_cols(arena, L[cur_li], R[L[cur_li].rel_in], (sweep & 1) ^ 1);
+          }
+          const RowCtx& c = sctx;
+          if (d.kind == TK_DIRECT) {
+            for (int r = 0; r < d.nrows; ++r) cle_row_generic(c, P, d.row0 + r, red, parity, dacc);
+          } else {
+            StagePub* pub = ws.pub + sidx;
+            cle_tile_smem(c, P, in_mode, buf, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr);
+          }
+          if (d.kind == TK_BULK) {
+            fence_proxy_async_smem();            // my generic-proxy writes -> visible to the bulk store
+          } else if (d.kind == TK_PLAIN) {
+            cbar();
+            for (int i = threadIdx.x; i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
+          }
+          mbar_arrive(ws.done + sidx);           // hand the tile back to the producer
+          count++;
+          it.next();
         }
-        const RowCtx& c = sctx;
-        if (d.kind == TK_DIRECT) {
-          for (int r = 0; r < d.nrows; ++r) cle_row_generic(c, P, d.row0 + r, red, parity, dacc);
-        } else {
-          cle_tile_smem(c, P, in_mode, pipe.stage[sidx], d.row0, d.nrows, s_inv, red, parity, dacc);
-        }
-        bool more = false;
-        if (threadIdx.x == 0) {
-          more = ahead.valid();
-          if (more) { ahead.fill(nd, arena); ahead.next(); }
-        }
-        pipe.release<true>(sidx, more, nd);
-        it.next();
+        flush();
       }
-      pipe.drain();
-      flush();
       grid.sync();
       mark();
       if (step_rescan[p]) {   // general middle layers of this step: round-robin over their scan tiles
-        long long sbase = 0;
-        for (int q = step_ptr[p]; q < step_ptr[p + 1]; ++q) {
-          const int li = step_layers[q];
-          if (L[li].col_mode == 2 && L[li].rel_in >= 0 && !*((volatile int*)&G[L[li].group].done)) {
-            const DfqRelation r = R[L[li].rel_in];
-            const long long nt = scan_tiles(r.groups, r.go);
-            long long first = ((long long)blockIdx.x - sbase) % (long long)gridDim.x;
-            if (first < 0) first += gridDim.x;
-            for (long long t = first; t < nt; t += gridDim.x)
-              scan_layer(arena, L, R, li, (sweep & 1) ^ 1, t, t + 1, smin, smax);
-            sbase += nt;
+        if (!producer) {
+          long long sbase = 0;
+          for (int q = step_ptr[p]; q < step_ptr[p + 1]; ++q) {
+            const int li = step_layers[q];
+            if (L[li].col_mode == 2 && L[li].rel_in >= 0 && !*((volatile int*)&G[L[li].group].done)) {
+              const DfqRelation r = R[L[li].rel_in];
+              const long long nt = scan_tiles(r.groups, r.go);
+              long long first = ((long long)blockIdx.x - sbase) % (long long)gridDim.x;
+              if (first < 0) first += gridDim.x;
+              for (long long t = first; t < nt; t += gridDim.x)
+                scan_layer(arena, L, R, li, (sweep & 1) ^ 1, t, t + 1, smin, smax);
+              sbase += nt;
+            }
           }
         }
         grid.sync();
@@ -583,21 +720,23 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
     }
     // ---- exit rule of dfq.py:105-115, one thread per group ------------------------------------------------
     const int n = sweep + 1;
-    for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) {
-      GroupState& st = G[g];
-      if (st.done) continue;
-      const double diff_tmp = st.acc[slot];
-      st.acc[(slot + 2) % 3] = 0.0;   // last read before this sweep's final barrier, next used in sweep+2
-      if (fabs(st.diff - diff_tmp) > 1e-9) { st.count = 0; st.diff = diff_tmp; }
-      else st.count++;
-      if (g == 0 && sweep < 64) ctl->diffs[sweep] = diff_tmp;
-      const bool cont = (st.diff > P.converge_thres) && (st.count < P.converge_count);
-      // safety net: the reference's loop has no bound; 4096 sweeps is ~80x what any of its models needs
-      const int cap = P.max_sweeps > 0 ? P.max_sweeps : 4096;
-      if (!cont || n >= cap) { st.n_sweeps = n; st.converged = !cont; st.done = 1; }
-      else atomicAdd(&ctl->active[n & 1], 1);
+    if (!producer) {
+      for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) {
+        GroupState& st = G[g];
+        if (st.done) continue;
+        const double diff_tmp = st.acc[slot];
+        st.acc[(slot + 2) % 3] = 0.0;   // last read before this sweep's final barrier, next used in sweep+2
+        if (fabs(st.diff - diff_tmp) > 1e-9) { st.count = 0; st.diff = diff_tmp; }
+        else st.count++;
+        if (g == 0 && sweep < 64) ctl->diffs[sweep] = diff_tmp;
+        const bool cont = (st.diff > P.converge_thres) && (st.count < P.converge_count);
+        // safety net: the reference's loop has no bound; 4096 sweeps is ~80x what any of its models needs
+        const int cap = P.max_sweeps > 0 ? P.max_sweeps : 4096;
+        if (!cont || n >= cap) { st.n_sweeps = n; st.converged = !cont; st.done = 1; }
+        else atomicAdd(&ctl->active[n & 1], 1);
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) ctl->active[sweep & 1] = 0;   // read at the end of the previous sweep
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->active[sweep & 1] = 0;   // read at the end of the previous sweep
     __threadfence();
     grid.sync();
     if (*((volatile int*)&ctl->active[n & 1]) == 0) break;
@@ -674,9 +813,9 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   DFQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DFQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) { set_error("device does not support cooperative launch"); return DFQ_E_NOT_COOPERATIVE; }
-  const size_t dyn_smem = RowPipe::smem_bytes();
+  const size_t dyn_smem = WsPipe::smem_bytes();
   DFQ_CUDA(cudaFuncSetAttribute(k_cle_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-  DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cle_engine, kThreads, dyn_smem));
+  DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cle_engine, kCtaThreads, dyn_smem));
   if (per_sm < 1) { set_error("persistent kernel does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
   const int grid = (int)std::min<int64_t>((int64_t)sms * per_sm, max_tiles);
 
@@ -712,7 +851,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   DfqCleParams P = *params;
   void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS,
                   &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups};
-  DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kThreads), args, dyn_smem, st));
+  DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kCtaThreads), args, dyn_smem, st));
   h_launch = ms_since(h0);
   CleCtl h;
   std::vector<GroupState> hg(n_groups);

@@ -108,9 +108,12 @@ def cross_layer_equalization(graph, relations, targ_type, s_range=[1e-8, 1e8], r
                 bn_bound[bn_idx] = (sess.bind(bn.fake_weight), sess.bind(bn.fake_bias))
             table.append((l1, l2) + bn_bound[bn_idx])
         sess.upload()
-        res, s_offs = sess.run_cle(table, s_range=s_range, converge_thres=converge_thres, converge_count=converge_count,
-                                   signed=signed, eps=eps)
-        scale_vecs = [sess.view(off, sess.layer(t[0])["rows"]).clone() for off, t in zip(s_offs, table)]
+        if _forward_chain_order(table):
+            res, s_offs = sess.run_cle(table, s_range=s_range, converge_thres=converge_thres, converge_count=converge_count,
+                                       signed=signed, eps=eps)
+            scale_vecs = [sess.view(off, sess.layer(t[0])["rows"]).clone() for off, t in zip(s_offs, table)]
+        else:
+            res, scale_vecs = _equalize_any_order(sess, table, s_range, converge_thres, converge_count, signed, eps)
         sess.download()
         for rr, S in zip(relations, scale_vecs):
             first = rr.get_idxs()[0]
@@ -119,6 +122,53 @@ def cross_layer_equalization(graph, relations, targ_type, s_range=[1e-8, 1e8], r
             if visualize_state:
                 visualize_per_layer(graph[first].weight.detach(), 'After equalization')
         cross_layer_equalization.last_result = res
+
+
+def _forward_chain_order(table):
+    """True when the fused persistent kernel applies: every layer is `first` of at most one relation and `second` of at
+    most one, and a layer's incoming relation precedes its outgoing one (what create_relation emits)."""
+    as_first, as_second = {}, {}
+    for i, (a, b, _, _) in enumerate(table):
+        if a in as_first or b in as_second:
+            return False
+        as_first[a] = i
+        as_second[b] = i
+    return all(as_second[l] < as_first[l] for l in as_first if l in as_second)
+
+
+def _equalize_any_order(sess, table, s_range, converge_thres, converge_count, signed, eps):
+    """Relation lists in an arbitrary order (hand-written lists; never produced by create_relation): the Gauss-Seidel
+    order of dfq.py:85-103 is kept by running ONE relation per launch (dfq_cle_run with max_sweeps=1), and the exit rule of
+    dfq.py:105-115 on the host from dfq_mean_abs_diff over device snapshots.  Slow path: one launch per relation."""
+    import ctypes as C
+    from .engine import CleResult
+    lib = _lib.load()
+    plans = [sess.plan_cle([t]) for t in table]
+    sess._ensure_room()
+    layers = sorted({t[0] for t in table} | {t[1] for t in table})
+    S = [None] * len(table)
+    out = torch.zeros(1, dtype=torch.float64, device=sess.device)
+    diff, count, n, diffs = 10, 0, 0, []
+    while diff > converge_thres and count < converge_count:
+        prev = {l: sess.view(sess.layer(l)["w_off"], sess.layer(l)["rows"] * sess.layer(l)["cols"] * sess.layer(l)["kk"]).clone()
+                for l in layers}
+        for i, plan in enumerate(plans):
+            sess.run_cle_plan(plan, s_range, converge_thres, converge_count, signed, eps, max_sweeps=1)
+            s = sess.view(plan["s_offs"][0], sess.layer(table[i][0])["rows"]).clone()
+            S[i] = s if S[i] is None else S[i] * s                       # relation.py:20-24
+        diff_tmp = 0.0
+        for l in layers:
+            cur = sess.view(sess.layer(l)["w_off"], prev[l].numel())
+            _lib.check(lib.dfq_mean_abs_diff(_ptr(cur), _ptr(prev[l]), prev[l].numel(), C.c_void_p(out.data_ptr()),
+                                             _lib.stream_ptr()), "dfq_mean_abs_diff")
+            diff_tmp += float(out.item())
+        diffs.append(diff_tmp)
+        n += 1
+        if abs(diff - diff_tmp) > 1e-9:
+            count, diff = 0, diff_tmp
+        else:
+            count += 1
+    return CleResult(n, True, float(diff), diffs), S
 
 
 def bias_absorption(graph, relations, bottoms, N=3):

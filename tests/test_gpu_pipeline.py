@@ -150,3 +150,51 @@ def test_quant_modules_forward_on_gpu_matches_torch_eager_reference_chain():
     qb = b.clone().add_(-bmn).div_(bs).clamp_(0., 65535.).round_().mul_(bs).add_(bmn)
     ref = torch.nn.functional.conv2d(qx, qw, qb, 1, 1)
     assert torch.allclose(y, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_graph_calibration_matches_separate_calls_on_gpu():
+    from dfq_b200 import dfq
+    from dfq_b200.calibrate import GraphCalibration
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    topo = workload.load_topology(os.path.join(GOLD, "topology_mobilenetv2.json"))
+    ga, ba, _ = workload.build_graph(topo, seed=21)
+    gb, bb, _ = workload.build_graph(topo, seed=21)
+    LT.merge_batchnorm(None, ga, ba, TARG)
+    rels = create_relation(ga, ba, TARG)
+    dfq.cross_layer_equalization(ga, rels, TARG)
+    dfq.bias_correction(ga, ba, TARG)
+    LT.quantize_targ_layer(ga, 8, 16, TARG)
+    cal = GraphCalibration(gb, bb, TARG)
+    res = cal.run(equalize=True, correction=True, quantize_bits=(8, 16))
+    assert res.n_sweeps == dfq.cross_layer_equalization.last_result.n_sweeps
+    for ra, rb in zip(rels, cal.relations):
+        assert np.array_equal(ra.S.numpy(), rb.S.numpy())
+    for ma, mb in zip(ga.values(), gb.values()):
+        if type(ma) in TARG:
+            assert np.array_equal(ma.weight.detach().numpy(), mb.weight.detach().numpy())
+            assert np.array_equal(ma.bias.detach().numpy(), mb.bias.detach().numpy())
+
+
+def test_relations_in_arbitrary_order_use_the_per_relation_path():
+    """A hand-written relation list that is NOT in forward chain order must still follow dfq.py's Gauss-Seidel order."""
+    from dfq_b200 import dfq
+    from dfq_b200.utils.relation import Relation
+    from oracle import dfq_oracle as O
+    torch.manual_seed(3)
+    convs = [nn.Conv2d(8, 16, 3, bias=True), nn.Conv2d(16, 12, 3, bias=True), nn.Conv2d(12, 10, 3, bias=False)]
+    bns = [nn.BatchNorm2d(16), nn.BatchNorm2d(12)]
+    for bn in bns:
+        bn.register_buffer("fake_weight", torch.rand(bn.num_features) + 0.5)
+        bn.register_buffer("fake_bias", torch.randn(bn.num_features))
+    graph = {0: convs[0], 1: bns[0], 2: convs[1], 3: bns[1], 4: convs[2]}
+    rels = [Relation(2, 4, 3), Relation(0, 2, 1)]          # backward order
+    layers = [O.OLayer(c.weight.detach().numpy().copy(), None if c.bias is None else c.bias.detach().numpy().copy()) for c in convs]
+    obns = [(b.fake_weight.numpy().copy(), b.fake_bias.numpy().copy()) for b in bns]
+    n_ref, _ = O.cross_layer_equalization(layers, obns, [O.ORelation(1, 2, 1), O.ORelation(0, 1, 0)])
+    dfq.cross_layer_equalization(graph, rels, [nn.Conv2d])
+    assert dfq.cross_layer_equalization.last_result.n_sweeps == n_ref
+    for c, l in zip(convs, layers):
+        assert np.array_equal(c.weight.detach().numpy(), l.w)
+        if l.b is not None:
+            assert np.array_equal(c.bias.detach().numpy(), l.b)

@@ -217,3 +217,41 @@ def test_graph_calibration_equals_the_four_separate_calls(monkeypatch):
             assert np.array_equal(ma.fake_bias.numpy(), mb.fake_bias.numpy())
             assert np.array_equal(ma.fake_weight.numpy(), mb.fake_weight.numpy())
             assert float(mb.weight.min()) == 1.0 and float(mb.running_var.max()) == 1.0 and mb.eps in (0, 1e-12)
+
+
+@pytest.mark.parametrize("name,seed", [("resnet18", 3), ("mobilenetv2", 0)])
+def test_set_quant_minmax_matches_reference_fixture(monkeypatch, name, seed):
+    """Data-free activation ranges (layer_transform.py:347-609) on the full graphs: every layer observer and every
+    functional-op observer (residual adds, the pooling mean) must get the reference's running_min / running_max."""
+    fakelib.install(monkeypatch, fakelib.torch_sqrt)
+    from dfq_b200 import dfq
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils import quantize as Q
+    from dfq_b200.utils.relation import create_relation
+    gold = np.load(os.path.join(GOLD, "ref_minmax_%s.npz" % name))
+    topo = workload.load_topology(os.path.join(GOLD, "topology_%s.json" % name))
+    graph, bottoms, _ = workload.build_graph(topo, seed=seed, conv_cls=Q.QuantNConv2d, linear_cls=Q.QuantNLinear)
+    targ = [Q.QuantNConv2d, Q.QuantNLinear]
+    record = [tuple(x) for x in topo["tensor_ops"]]
+    ops = []
+    for _, op_name in record:
+        ops.extend(Q.QuantMeasure(num_bits=8, momentum=0.1) for _ in range(int(op_name.split('_')[-1])))
+    monkeypatch.setattr(LT, "module_tensor_op", LT.CustomTensorOP(ops, record))
+    LT.merge_batchnorm(None, graph, bottoms, targ)
+    rels = create_relation(graph, bottoms, targ)
+    dfq.cross_layer_equalization(graph, rels, targ, converge_thres=2e-7)
+    dfq.bias_correction(graph, bottoms, targ)
+    LT.set_quant_minmax(graph, bottoms, verbose=False)
+    n = 0
+    for i, k in enumerate(graph):
+        m = graph[k]
+        if hasattr(m, "quant") and not isinstance(m, str):
+            want = gold["layer_%d" % i]
+            got = np.array([float(m.quant.running_min), float(m.quant.running_max)])
+            assert np.allclose(got, want, rtol=3e-4, atol=1e-5, equal_nan=True), (i, got, want)   # downstream of the fp32-BLAS bias correction
+            n += 1
+    for j, qm in enumerate(ops):
+        want = gold["op_%d" % j]
+        got = np.array([float(qm.running_min), float(qm.running_max)])
+        assert np.allclose(got, want, rtol=3e-4, atol=1e-5, equal_nan=True), ("op", j, got, want)
+    assert n + len(ops) == len(gold.files)

@@ -218,3 +218,56 @@ if __name__ == "__main__":
         run_reference_pipeline("deeplab", seed=5)
     if "ssd" in what:
         run_reference_pipeline("ssd", seed=7, delete_single=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def quant_minmax_fixture(name="mobilenetv2", seed=0):
+    """set_quant_minmax (layer_transform.py:347-609) needs the tracer's record of functional ops; trace the reference
+    model with Quant layers + observers, store the op record with the topology, run the reference calibration on the
+    seeded topology-built graph and store every observer's running_min / running_max."""
+    TT = refenv.tracer()
+    Q = ref.quantize
+    if name == "mobilenetv2":
+        from modeling.classification.MobileNetV2 import mobilenet_v2
+        model, data = mobilenet_v2(None), torch.ones((4, 3, 224, 224))
+    elif name == "resnet18":
+        import torchvision.models as models
+        model, data = models.resnet18(), torch.ones((4, 3, 224, 224))
+    model.eval()
+    tr = TT()
+    md = {0: [(nn.ReLU6, nn.ReLU)], 1: [(nn.Conv2d, Q.QuantNConv2d), (nn.Linear, Q.QuantNLinear)]}
+    model, tr = ref.layer_transform.switch_layers(model, tr, data, md, ignore_layer=[Q.QuantMeasure], quant_op=True)
+    record = [list(x) for x in model.name_tensor_op]
+    topo = workload.load_topology(os.path.join(GOLD, "topology_%s.json" % name))
+    graph0 = tr.log.getGraph()
+    assert len(graph0) == len(topo["nodes"]), (len(graph0), len(topo["nodes"]))
+    topo["tensor_ops"] = record
+    with open(os.path.join(GOLD, "topology_%s.json" % name), "w") as f:
+        json.dump(topo, f, separators=(",", ":"))
+    # reference calibration on the seeded graph built from the topology, with the reference's own Quant classes
+    graph, bottoms, _ = workload.build_graph(topo, seed=seed, conv_cls=Q.QuantNConv2d, linear_cls=Q.QuantNLinear)
+    targ = [Q.QuantNConv2d, Q.QuantNLinear]
+    LT = ref.layer_transform
+    ops = []
+    for _, op_name in record:
+        ops.extend(Q.QuantMeasure(num_bits=8, momentum=0.1) for _ in range(int(op_name.split('_')[-1])))
+    LT.module_tensor_op = LT.CustomTensorOP(ops, [tuple(x) for x in record])
+    LT.merge_batchnorm(None, graph, bottoms, targ)
+    rels = ref.relation.create_relation(graph, bottoms, targ)
+    ref.dfq.cross_layer_equalization(graph, rels, targ, converge_thres=2e-7)
+    ref.dfq.bias_correction(graph, bottoms, targ)
+    LT.set_quant_minmax(graph, bottoms, verbose=False)
+    out = {}
+    for i, k in enumerate(graph):
+        m = graph[k]
+        if hasattr(m, "quant") and not isinstance(m, str):
+            out["layer_%d" % i] = np.array([float(m.quant.running_min), float(m.quant.running_max)])
+    for j, qm in enumerate(ops):
+        out["op_%d" % j] = np.array([float(qm.running_min), float(qm.running_max)])
+    np.savez_compressed(os.path.join(GOLD, "ref_minmax_%s.npz" % name), **out)
+    print("minmax", name, len(out), "observers;", len(record), "functional ops")
+
+
+if __name__ == "__main__" and "minmax" in sys.argv[1:]:
+    quant_minmax_fixture("mobilenetv2", 0)
+    quant_minmax_fixture("resnet18", 3)
