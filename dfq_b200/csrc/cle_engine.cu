@@ -65,6 +65,7 @@ struct CleCtl {
   double diffs[64];  // diff_tmp per sweep of group 0
   unsigned long long t_ns[16];  // %globaltimer at phase boundaries (block 0), printed when DFQ_TRACE is set
   int grid, per_sm;
+  unsigned long long tile_ns[48][8];  // per-tile timeline of block 0 in the first pass (DFQ_TRACE): consumer 0-3, producer 4-7
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -519,8 +520,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 //   lane 1  per-channel bookkeeping of tile m (publish_row: S, 1/s, bias, BN vectors, derived column extrema)
 //   lane 2  prefetch of the new tile's column extrema into its mailbox
 __device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
-                           unsigned long long& count, const DfqCleParams& P, int sweep) {
+                           unsigned long long& count, const DfqCleParams& P, int sweep, CleCtl* ctl, bool tr) {
   const int lane = threadIdx.x & 31;
+  const unsigned long long count0 = count;
   unsigned long long n = count, m = count;     // next tile to issue / to retire (uniform across the warp)
   RowCtx ctx;                                  // lane 1: layer being retired; lane 2: layer being issued
   int li = -1;
@@ -531,6 +533,7 @@ __device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R
     if (do_retire) {
       const int sr = (int)(m % kPipeStages);
       mbar_wait(ws.done + sr, (uint32_t)((m / kPipeStages) & 1));          // the consumers are done with tile m
+      if (tr && lane == 0 && m - count0 < 48) ctl->tile_ns[m - count0][4] = gtimer();
       const TileDesc d = ws.desc[sr];
       const StagePub pb = ws.pub[sr];
       __syncwarp();                                                          // everyone holds a copy before the stage is recycled
@@ -538,6 +541,7 @@ __device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R
         bulk_s2g(d.gptr, ws.stage[sr], (uint32_t)d.floats * 4u);
         bulk_commit();
         bulk_wait_read<0>();                                                 // the stage may be overwritten now
+        if (tr && m - count0 < 48) ctl->tile_ns[m - count0][5] = gtimer();
       }
       if (lane == 1 && pb.valid) {
         if (d.task != li) { make_ctx(ctx, arena, L, R, d.task, sweep); li = d.task; }
@@ -556,6 +560,7 @@ __device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R
           mbar_expect_tx(ws.full + si, (uint32_t)d.floats * 4u);
           bulk_g2s(ws.stage[si], d.gptr, (uint32_t)d.floats * 4u, ws.full + si);
         }
+        if (tr && n - count0 < 48) ctl->tile_ns[n - count0][6] = gtimer();
       }
       if (lane == 2) {
         StagePub pb; pb.valid = 0; pb.cmn = pb.cmx = pb.s = pb.inv = 0.f;
@@ -566,7 +571,10 @@ __device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R
         ws.pub[si] = pb;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(ws.full + si);   // phase completes when this arrival AND the bulk bytes have landed
+      if (lane == 0) {
+        mbar_arrive(ws.full + si);   // phase completes when this arrival AND the bulk bytes have landed
+        if (tr && n - count0 < 48) ctl->tile_ns[n - count0][7] = gtimer();
+      }
       n++;
     }
     __syncwarp();
@@ -629,7 +637,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
       PassIter it;
       it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
       if (producer) {
-        ws_produce(arena, L, R, it, ws, count, P, sweep);
+        ws_produce(arena, L, R, it, ws, count, P, sweep, ctl, blockIdx.x == 0 && sweep == 0 && p == 0);
       } else {
         double dacc = 0.0;
         int cur_g = -1;
@@ -649,9 +657,13 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
           dacc = 0.0;
         };
         int cur_li = -1, in_mode = IN_NONE;
+        const bool tr = (blockIdx.x == 0 && threadIdx.x == 0 && sweep == 0 && p == 0);
+        int trn = 0;
         while (it.valid()) {
           const int sidx = (int)(count % kPipeStages);
+          if (tr && trn < 48) ctl->tile_ns[trn][0] = gtimer();
           mbar_wait(ws.full + sidx, (uint32_t)((count / kPipeStages) & 1));
+          if (tr && trn < 48) ctl->tile_ns[trn][1] = gtimer();
           const TileDesc d = ws.desc[sidx];
           float* buf = ws.stage[sidx];
           if (d.kind == TK_PLAIN) {            // a tile the TMA unit cannot move: cooperative fetch
@@ -685,6 +697,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
             StagePub* pub = ws.pub + sidx;
             cle_tile_smem(c, P, in_mode, buf, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr);
           }
+          if (tr && trn < 48) ctl->tile_ns[trn][2] = gtimer();
           if (d.kind == TK_BULK) {
             fence_proxy_async_smem();            // my generic-proxy writes -> visible to the bulk store
           } else if (d.kind == TK_PLAIN) {
@@ -692,6 +705,8 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
             for (int i = threadIdx.x; i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
           }
           mbar_arrive(ws.done + sidx);           // hand the tile back to the producer
+          if (tr && trn < 48) ctl->tile_ns[trn][3] = gtimer();
+          trn++;
           count++;
           it.next();
         }
@@ -873,6 +888,15 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     fprintf(stderr, "[dfq_cle_run] grid %d (%d CTAs/SM) sweeps %d; phase ms:", grid, per_sm, result->n_sweeps);
     for (int i = 1; i < 16 && h.t_ns[i]; ++i) fprintf(stderr, " %.3f", (h.t_ns[i] - h.t_ns[i - 1]) * 1e-6);
     fprintf(stderr, "\n");
+    if (getenv("DFQ_TRACE_TILES")) {
+      const unsigned long long t0 = h.tile_ns[0][6];
+      fprintf(stderr, "tile: C.wait C.ready C.done C.arrived | P.retire P.stored P.loadissued P.fullarrive  (us since first load)\n");
+      for (int i = 0; i < 48; ++i) {
+        fprintf(stderr, "%3d:", i);
+        for (int j = 0; j < 8; ++j) fprintf(stderr, " %8.2f", h.tile_ns[i][j] ? (double)(h.tile_ns[i][j] - t0) * 1e-3 : -1.0);
+        fprintf(stderr, "\n");
+      }
+    }
   }
   result->last_diff = hg[0].diff;
   memcpy(result->diffs, h.diffs, sizeof(h.diffs));

@@ -367,6 +367,12 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
         const int o = d.row0;
         const float* row = (d.kind == TK_DIRECT) ? d.gptr : pipe.stage[sidx];
         const float* ex = (ex_cached ? s_ex : arena + b.expect_off) + (size_t)(o / so) * l.cols;
+        // the leader's read-modify-write operands are requested before the row is processed: their latency is hidden
+        float old_bias = 0.f, old_next = 0.f;
+        if (threadIdx.x == 0) {
+          old_bias = __ldcg(arena + l.bias_off + o);
+          if (b.next_bn_b_off >= 0) old_next = __ldcg(arena + b.next_bn_b_off + o);
+        }
         double acc = raw ? bc_row<kThreads, true>(row, l.cols, l.kk, ex, q, threadIdx.x)
                          : bc_row<kThreads, false>(row, l.cols, l.kk, ex, q, threadIdx.x);
         if (lane == 0) dred[warp] = acc;
@@ -377,9 +383,8 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
           for (int i = 0; i < kWarps; ++i) acc += dred[i];
           const float dl = (float)acc;
           __stcg(arena + b.delta_off + o, dl);
-          __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), (b.flags & 2) ? dl : -dl));   // dfq.py:292 / :164
-          if (b.next_bn_b_off >= 0)                                                                    // dfq.py:204-206,293
-            __stcg(arena + b.next_bn_b_off + o, __fadd_rn(__ldcg(arena + b.next_bn_b_off + o), -dl));
+          __stcg(arena + l.bias_off + o, __fadd_rn(old_bias, (b.flags & 2) ? dl : -dl));              // dfq.py:292 / :164
+          if (b.next_bn_b_off >= 0) __stcg(arena + b.next_bn_b_off + o, __fadd_rn(old_next, -dl));   // dfq.py:204-206,293
         }
       } else {
         for (int r = warp; r < d.nrows; r += kWarps) {

@@ -255,3 +255,51 @@ def test_set_quant_minmax_matches_reference_fixture(monkeypatch, name, seed):
         got = np.array([float(qm.running_min), float(qm.running_max)])
         assert np.allclose(got, want, rtol=3e-4, atol=1e-5, equal_nan=True), ("op", j, got, want)
     assert n + len(ops) == len(gold.files)
+
+
+def test_live_ncnn_table_through_the_product_host_path(monkeypatch):
+    """The reference's checked-in calibration table (modeling/ncnn/model_quant_relu_equal.table = `--quantize --relu
+    --equalize`, convert_ncnn.py) reproduced by THIS package's entry points end to end - merge_batchnorm, create_relation,
+    signed cross_layer_equalization, set_quant_minmax, export.ncnn_scales - on the bundled MobileNetV2 checkpoint:
+    53 weight-scale rows and 53 activation-scale rows.  (Arithmetic by the oracle-backed fake ABI; reference tree needed.)"""
+    ref_root = os.environ.get("DFQ_REFERENCE_ROOT", "/root/reference")
+    table = os.path.join(ref_root, "modeling", "ncnn", "model_quant_relu_equal.table")
+    ckpt = os.path.join(ref_root, "modeling", "classification", "mobilenetv2_1.0-f2a8633.pth.tar")
+    if not (os.path.isfile(table) and os.path.isfile(ckpt)):
+        pytest.skip("reference tree not present")
+    fakelib.install(monkeypatch, fakelib.torch_sqrt)
+    from dfq_b200 import dfq, export
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils import quantize as Q
+    from dfq_b200.utils.relation import create_relation
+    rows = [l.split() for l in open(table).read().strip().splitlines()]
+    gold_w = np.array([float(r[1]) for r in rows[:53]])
+    gold_a = np.array([float(r[1]) for r in rows[53:106]])
+    topo = workload.load_topology(os.path.join(GOLD, "topology_mobilenetv2.json"))
+    graph, bottoms, modules = workload.build_graph(topo, seed=0, conv_cls=Q.QuantNConv2d, linear_cls=Q.QuantNLinear)
+    sd = torch.load(ckpt, map_location="cpu")
+    it = iter([v for k, v in sd.items() if "num_batches_tracked" not in k])
+    with torch.no_grad():
+        for m in modules:
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                m.weight.copy_(next(it))
+                if m.bias is not None:
+                    m.bias.copy_(next(it))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.copy_(next(it)); m.bias.copy_(next(it)); m.running_mean.copy_(next(it)); m.running_var.copy_(next(it))
+    targ = [Q.QuantNConv2d, Q.QuantNLinear]
+    record = [tuple(x) for x in topo["tensor_ops"]]
+    ops = []
+    for _, op_name in record:
+        ops.extend(Q.QuantMeasure(num_bits=8, momentum=0.1) for _ in range(int(op_name.split('_')[-1])))
+    monkeypatch.setattr(LT, "module_tensor_op", LT.CustomTensorOP(ops, record))
+    Q.set_layer_bits(graph, 8, 8, 8, targ)
+    LT.merge_batchnorm(None, graph, bottoms, targ)
+    rels = create_relation(graph, bottoms, targ)
+    dfq.cross_layer_equalization(graph, rels, targ, converge_thres=2e-7, signed=True)
+    LT.set_quant_minmax(graph, bottoms, verbose=False)
+    scales = export.ncnn_scales(graph, targ)
+    got_w = np.array([s[0] for s in scales]); got_a = np.array([s[2] for s in scales])
+    assert got_w.shape == gold_w.shape and got_a.shape == gold_a.shape
+    assert np.abs(got_w / gold_w - 1).max() < 2e-6, np.abs(got_w / gold_w - 1).max()
+    assert np.abs(got_a / gold_a - 1).max() < 5e-6, np.abs(got_a / gold_a - 1).max()
