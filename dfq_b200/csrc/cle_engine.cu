@@ -37,17 +37,44 @@ namespace dfq {
 
 // CTA = 7 consumer warps (the arithmetic) + 1 producer warp (TMA loads/stores and the per-row scalar bookkeeping),
 // see "warp-specialised pass" below.  kThreads / kWarps count the CONSUMERS: every tile loop and reduction strides by them.
-constexpr int kThreads = 224;
+#ifndef DFQ_CONSUMERS
+#define DFQ_CONSUMERS 224
+#endif
+// ring geometry of THIS kernel (rowpipe.cuh's kPipeStages / kPipeCtas configure the simpler fold / bias-correction pipes)
+#ifndef DFQ_CLE_STAGES
+#define DFQ_CLE_STAGES 3
+#endif
+#ifndef DFQ_CLE_CTAS
+#define DFQ_CLE_CTAS 3
+#endif
+constexpr int kCleStages = DFQ_CLE_STAGES;   // stages per CTA
+constexpr int kCleCtas = DFQ_CLE_CTAS;       // co-resident CTAs per SM the kernel is compiled for
+#ifndef DFQ_TEAMS
+#define DFQ_TEAMS 1
+#endif
+// Consumer TEAMS: kTeams groups of kThreads threads, each working on its own tile (own named barrier, own context and
+// caches), fed in turn from the one ring the producer warp fills: tile n of the CTA goes to team n % kTeams.
+constexpr int kTeams = DFQ_TEAMS;
+constexpr int kThreads = DFQ_CONSUMERS;      // per team
 constexpr int kWarps = kThreads / 32;
-constexpr int kCtaThreads = kThreads + 32;
-// barrier among the consumer warps only (the producer warp never joins it)
-__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+constexpr int kCtaThreads = kTeams * kThreads + 32;
+static_assert(kThreads % 32 == 0 && kWarps <= 8 && kTeams >= 1 && kTeams <= 8, "team geometry");
+__device__ __forceinline__ int ctid() { return kTeams == 1 ? (int)threadIdx.x : (int)(threadIdx.x % kThreads); }   // thread within its team
+__device__ __forceinline__ int team() { return kTeams == 1 ? 0 : (int)(threadIdx.x / kThreads); }
+// a team is a virtual CTA for everything that is distributed per CTA outside the ring
+__device__ __forceinline__ int vblock() { return blockIdx.x * kTeams + team(); }
+__device__ __forceinline__ int vgrid() { return gridDim.x * kTeams; }
+// barrier among the warps of one team only (the producer warp never joins it)
+__device__ __forceinline__ void cbar() {
+  if (kTeams == 1) asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + team()), "n"(kThreads) : "memory");
+}
 constexpr int kScanRows = 32;      // rows per column-scan tile
-constexpr int kScanCols = 2048;    // columns kept in shared memory by a scan tile
 #ifndef DFQ_INV_CACHE
 #define DFQ_INV_CACHE 2044
 #endif
 constexpr int kInvCache = DFQ_INV_CACHE;    // reciprocal scales of a layer's input columns cached in shared memory
+constexpr int kScanCols = (kInvCache + 4) / 2 < 1024 ? (kInvCache + 4) / 2 : 1024;   // columns a scan keeps in shared memory (aliases that cache)
 
 // Convergence state of one GROUP of chains.  The reference's exit rule (dfq.py:81-115) is evaluated per model: one
 // group.  A batch of independent models (the synthetic stack: every block is its own model) is calibrated in one
@@ -100,7 +127,7 @@ struct RowCtx {
 };
 
 // dfq.py:58-59 + :73.  Returns s; *inv is the factor applied to the columns of the second layer.
-__device__ __forceinline__ float solve_scale(float r1, float r2, const DfqCleParams& P, float* inv) {
+__device__ __forceinline__ float solve_scale(float r1, float r2, const DfqCleParams P, float* inv) {
   const float a = __frcp_rn(__fadd_rn(r1, P.eps));
   const float b = __fsqrt_rn(__fadd_rn(__fmul_rn(r1, r2), P.eps));
   const float s = __fmul_rn(a, b);
@@ -126,7 +153,7 @@ __device__ __forceinline__ int col_of(int e, int kk) {
 __device__ __forceinline__ void cta_minmax(float& mn, float& mx, float* red, int& parity) {
   mn = warp_min(mn);
   mx = warp_max(mx);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int w = ctid() >> 5, l = ctid() & 31;
   float* r = red + (parity & 1) * 2 * kWarps;
   parity++;
   if (l == 0) { r[w] = mn; r[kWarps + w] = mx; }
@@ -143,7 +170,7 @@ __device__ __forceinline__ void cta_minmax(float& mn, float& mx, float* red, int
 struct StagePub { float cmn, cmx, s, inv; int valid; int pad[3]; };
 
 // The per-channel bookkeeping of dfq.py:62-70 + relation.py:20-24 + the derived column extrema, for ONE channel.
-__device__ __forceinline__ void publish_row(const RowCtx& c, const DfqCleParams& P, int o, float s, float inv, float cmn, float cmx) {
+__device__ __forceinline__ void publish_row(const RowCtx& c, const DfqCleParams P, int o, float s, float inv, float cmn, float cmx) {
   c.s_step[o] = s;
   __stcg(c.inv_out + o, inv);
   if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(__ldcg(c.s_acc + o), s);
@@ -161,7 +188,7 @@ __device__ __forceinline__ void publish_row(const RowCtx& c, const DfqCleParams&
 }
 
 // All threads of the row's group call this with the reduced row extrema; the leader publishes.
-__device__ __forceinline__ float solve_only(const RowCtx& c, const DfqCleParams& P, int o, float mn, float mx, float cmn,
+__device__ __forceinline__ float solve_only(const RowCtx& c, const DfqCleParams P, int o, float mn, float mx, float cmn,
                                             float cmx, float* inv) {
   if (P.apply_only) {          // replay a given scale vector (multi-GPU replicas): s = S[o], columns get 1/S[o]
     const float s = __ldcg(c.s_acc + o);
@@ -170,7 +197,7 @@ __device__ __forceinline__ float solve_only(const RowCtx& c, const DfqCleParams&
   }
   return solve_scale(range_of(mn, mx, P.signed_mode), range_of(cmn, cmx, P.signed_mode), P, inv);
 }
-__device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCleParams& P, int o,
+__device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCleParams P, int o,
                                                    float mn, float mx, float cmn, float cmx, bool leader) {
   float inv;
   const float s = solve_only(c, P, o, mn, mx, cmn, cmx, &inv);
@@ -214,97 +241,160 @@ __device__ __forceinline__ float in_scale1(float t, int e, const float* __restri
   return t;
 }
 
-// One row resident in shared memory: [range reduction -> s] (HAS_OUT) then rescale IN PLACE, accumulating |new - old|.
-// Everything the loops need is copied into registers first: `row` stores could alias the context in shared memory,
-// which would force the compiler to reload it after every store.
+// float4 slots a thread keeps in registers between the range reduction and the rescale (kThreads * kRowRegs * 4 >= kStageFloats)
+constexpr int kRowRegs = (kStageFloats / 4 + kThreads - 1) / kThreads;
+// How a rescaled row leaves the SM:  1 = written back into its stage, the producer warp bulk-stores the tile (TMA);
+// 0 = straight from the consumers' registers with streaming stores (the stage is released as soon as the row is in registers).
+#ifndef DFQ_TMA_STORE
+#define DFQ_TMA_STORE 1
+#endif
+constexpr bool kTmaStore = DFQ_TMA_STORE != 0;
+constexpr int TK_END = 3;   // sentinel tile: the pass is over for this CTA (the consumers keep no iterator of their own)
+static_assert(kThreads * kRowRegs * 4 >= kStageFloats, "a single-row tile must fit the consumers' registers");
+
+// One row resident in shared memory (read-only here): [range reduction -> s] (HAS_OUT), rescale, accumulate |new - old|,
+// and write the new row STRAIGHT to global memory.  The stage is read ONCE when the row fits the registers (always for the
+// CTA-wide single-row tiles): shared-memory bandwidth, not HBM, was the limit when the row was re-read and written back
+// for a bulk store (5 shared-memory touches per HBM byte; now 2).  `done`: the stage's consumer->producer barrier, arrived
+// as soon as this thread no longer needs the stage (nullptr: the caller arrives).
 template <int TPR, int MODE, bool HAS_OUT>
-__device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams& P, float* __restrict__ row, int o, int lane,
-                                             const float* __restrict__ s_inv, float* red, int& parity, double& dacc,
-                                             StagePub* pub = nullptr) {
+__device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams P, float* __restrict__ row,
+                                             float* __restrict__ grow, int o, int lane, const float* __restrict__ s_inv,
+                                             float* red, int& parity, double& dacc, StagePub* pub, uint64_t* done) {
   const int n = c.row_len, kk = c.kk;
-  const bool vec = ((n & 3) == 0);
+  const bool vec = ((n & 3) == 0) && (kTmaStore || (((uintptr_t)grow) & 15) == 0);
+  auto put4 = [&](int i4, const float4& t) { if (kTmaStore) ((float4*)row)[i4] = t; else stg_stream((float4*)grow + i4, t); };
+  auto put1 = [&](int e, float t) { if (kTmaStore) row[e] = t; else stg_stream1(grow + e, t); };
+  const int n4 = n >> 2;
   const double inv_n = c.inv_n;
   const float* inv = nullptr;
   float u = 1.f;
   if (MODE == IN_UNIFORM) u = __ldcg(c.inv_in + (o / c.in_go) * c.in_gi);
   else if (MODE == IN_KK1 || MODE == IN_KK9) inv = s_inv;
   else if (MODE == IN_GENERIC) inv = c.inv_in + (o / c.in_go) * c.in_gi;
-  float s = 1.f;
+  float s = 1.f, cmn = 0.f, cmx = 0.f;
   if (HAS_OUT) {
-    float cmn, cmx;
     if (pub) { cmn = pub->cmn; cmx = pub->cmx; }                             // prefetched by the producer warp
     else { cmn = __ldcg(c.cmin_rd + o); cmx = __ldcg(c.cmax_rd + o); }       // in flight during the reduction
-    float mn = DFQ_INF, mx = -DFQ_INF;
-    if (vec) {
-      const float4* r4 = (const float4*)row;
-      const int n4 = n >> 2;
+  }
+  // s from the reduced row extrema; single-row tiles leave the bookkeeping to the producer warp (mailbox)
+  auto solve = [&](float mn, float mx) {
+    if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
+    else cta_minmax(mn, mx, red, parity);
+    if (pub) {
+      float iv;
+      s = solve_only(c, P, o, mn, mx, cmn, cmx, &iv);
+      if (lane == 0) { pub->s = s; pub->inv = iv; }
+    } else {
+      s = solve_and_publish(c, P, o, mn, mx, cmn, cmx, lane == 0);
+    }
+  };
+  float dsum = 0.f;
+  // a row that only gets its columns scaled (no reduction to wait for) streams through the in-place loop further down when
+  // the tile leaves by bulk store: holding it in registers buys nothing there and measured ~12% slower
+  if (vec && n4 <= TPR * kRowRegs && (HAS_OUT || !kTmaStore)) {
+    const float4* r4 = (const float4*)row;
+    float4 v[kRowRegs];
+#pragma unroll
+    for (int k = 0; k < kRowRegs; ++k) {
+      const int i4 = lane + k * TPR;
+      v[k] = (i4 < n4) ? r4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (HAS_OUT) {
+      float mn = DFQ_INF, mx = -DFQ_INF;
+#pragma unroll
+      for (int k = 0; k < kRowRegs; ++k) {
+        const int i4 = lane + k * TPR;
+        if (i4 < n4) {
+          const float4 t = in_scale4<MODE>(v[k], i4 * 4, inv, u, kk);
+          mn = fminf(mn, fminf(fminf(t.x, t.y), fminf(t.z, t.w)));
+          mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+        }
+      }
+      solve(mn, mx);
+      if (done) mbar_arrive(done);        // the row lives in registers: the stage can be refilled while it is rescaled
+    }
+#pragma unroll
+    for (int k = 0; k < kRowRegs; ++k) {
+      const int i4 = lane + k * TPR;
+      if (i4 < n4) {
+        float4 t = in_scale4<MODE>(v[k], i4 * 4, inv, u, kk);
+        if (HAS_OUT) { t.x = __fmul_rn(t.x, s); t.y = __fmul_rn(t.y, s); t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s); }
+        put4(i4, t);
+        dsum += fabsf(__fsub_rn(t.x, v[k].x)) + fabsf(__fsub_rn(t.y, v[k].y)) + fabsf(__fsub_rn(t.z, v[k].z)) +
+                fabsf(__fsub_rn(t.w, v[k].w));
+      }
+    }
+    if (!HAS_OUT && done) mbar_arrive(done);
+  } else if (vec) {
+    const float4* r4 = (const float4*)row;
+    if (HAS_OUT) {
+      float mn = DFQ_INF, mx = -DFQ_INF;
 #pragma unroll 2
       for (int i4 = lane; i4 < n4; i4 += TPR) {
         const float4 t = in_scale4<MODE>(r4[i4], i4 * 4, inv, u, kk);
         mn = fminf(mn, fminf(fminf(t.x, t.y), fminf(t.z, t.w)));
         mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
       }
-    } else {
-      for (int e = lane; e < n; e += TPR) {
-        const float t = in_scale1<MODE>(row[e], e, inv, u, kk);
-        mn = fminf(mn, t); mx = fmaxf(mx, t);
-      }
+      solve(mn, mx);
     }
-    if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
-    else cta_minmax(mn, mx, red, parity);
-    if (pub) {      // the producer warp does the bookkeeping after the tile is handed back
-      float inv;
-      s = solve_only(c, P, o, mn, mx, cmn, cmx, &inv);
-      if (lane == 0) { pub->s = s; pub->inv = inv; }
-    } else {
-      s = solve_and_publish(c, P, o, mn, mx, cmn, cmx, lane == 0);
-    }
-  }
-  float dsum = 0.f;
-  if (vec) {
-    float4* r4 = (float4*)row;
-    const int n4 = n >> 2;
 #pragma unroll 2
     for (int i4 = lane; i4 < n4; i4 += TPR) {
       const float4 v = r4[i4];
       float4 t = in_scale4<MODE>(v, i4 * 4, inv, u, kk);
       if (HAS_OUT) { t.x = __fmul_rn(t.x, s); t.y = __fmul_rn(t.y, s); t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s); }
-      r4[i4] = t;
+      put4(i4, t);
       dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
     }
+    if (done) mbar_arrive(done);
   } else {
+    if (HAS_OUT) {
+      float mn = DFQ_INF, mx = -DFQ_INF;
+      for (int e = lane; e < n; e += TPR) {
+        const float t = in_scale1<MODE>(row[e], e, inv, u, kk);
+        mn = fminf(mn, t); mx = fmaxf(mx, t);
+      }
+      solve(mn, mx);
+    }
     for (int e = lane; e < n; e += TPR) {
       const float v = row[e];
       float t = in_scale1<MODE>(v, e, inv, u, kk);
       if (HAS_OUT) t = __fmul_rn(t, s);
-      row[e] = t;
+      put1(e, t);
       dsum += fabsf(__fsub_rn(t, v));
     }
+    if (done) mbar_arrive(done);
   }
   dacc += (double)dsum * inv_n;
 }
 
+// A tile of whole rows in shared memory -> rescaled rows (in global memory at `g`, or in place for the bulk store);
+// every consumer thread arrives on `done` exactly once.
 template <int MODE, bool HAS_OUT>
-__device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams& P, float* buf, int row0, int nrows,
-                                              const float* s_inv, float* red, int& parity, double& dacc, StagePub* pub) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams P, float* buf, float* g, int row0,
+                                              int nrows, const float* s_inv, float* red, int& parity, double& dacc,
+                                              StagePub* pub, uint64_t* done) {
+  const int warp = ctid() >> 5, lane = ctid() & 31;
   if (nrows == 1) {
-    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, row0, threadIdx.x, s_inv, red, parity, dacc, HAS_OUT ? pub : nullptr);
+    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, g, row0, ctid(), s_inv, red, parity, dacc, HAS_OUT ? pub : nullptr,
+                                          kTmaStore ? nullptr : done);
   } else {
     const int row_len = c.row_len;
     for (int r = warp; r < nrows; r += kWarps)
-      cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, row0 + r, lane, s_inv, red, parity, dacc);
+      cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, g + (size_t)r * row_len, row0 + r, lane, s_inv, red,
+                                      parity, dacc, nullptr, nullptr);
+    if (!kTmaStore) mbar_arrive(done);
   }
 }
 
-__device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParams& P, int in_mode, float* buf, int row0,
-                                              int nrows, const float* s_inv, float* red, int& parity, double& dacc,
-                                              StagePub* pub) {
-#define DFQ_TILE(M)                                                                                   \
-  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub);       \
-  else cle_tile_rows<M, false>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub);
+__device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParams P, int in_mode, float* buf, float* g,
+                                              int row0, int nrows, const float* s_inv, float* red, int& parity, double& dacc,
+                                              StagePub* pub, uint64_t* done) {
+#define DFQ_TILE(M)                                                                                            \
+  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, g, row0, nrows, s_inv, red, parity, dacc, pub, done);       \
+  else cle_tile_rows<M, false>(c, P, buf, g, row0, nrows, s_inv, red, parity, dacc, pub, done);
   switch (in_mode) {
-    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub); break;
+    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, g, row0, nrows, s_inv, red, parity, dacc, pub, done); break;
     case IN_UNIFORM: DFQ_TILE(IN_UNIFORM) break;
     case IN_KK1: DFQ_TILE(IN_KK1) break;
     case IN_KK9: DFQ_TILE(IN_KK9) break;
@@ -314,23 +404,23 @@ __device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParam
 }
 
 // Any row length / alignment: CTA per row, the row is read twice (second read is an L2 hit).
-__device__ __forceinline__ void cle_row_generic(const RowCtx& c, const DfqCleParams& P, int o,
+__device__ __forceinline__ void cle_row_generic(const RowCtx& c, const DfqCleParams P, int o,
                                                 float* red, int& parity, double& dacc) {
   float* rowp = c.w + (size_t)o * c.row_len;
   const int cbase = c.inv_in ? (o / c.in_go) * c.in_gi : 0;
   float s = 1.f;
   if (c.has_out) {
     float mn = DFQ_INF, mx = -DFQ_INF;
-    for (int e = threadIdx.x; e < c.row_len; e += kThreads) {
+    for (int e = ctid(); e < c.row_len; e += kThreads) {
       float t = ldg_stream1(rowp + e);
       if (c.inv_in) t = __fmul_rn(t, __ldcg(c.inv_in + cbase + col_of(e, c.kk)));
       mn = fminf(mn, t); mx = fmaxf(mx, t);
     }
     cta_minmax(mn, mx, red, parity);
-    s = solve_and_publish(c, P, o, mn, mx, __ldcg(c.cmin_rd + o), __ldcg(c.cmax_rd + o), threadIdx.x == 0);
+    s = solve_and_publish(c, P, o, mn, mx, __ldcg(c.cmin_rd + o), __ldcg(c.cmax_rd + o), ctid() == 0);
   }
   float dsum = 0.f;
-  for (int e = threadIdx.x; e < c.row_len; e += kThreads) {
+  for (int e = ctid(); e < c.row_len; e += kThreads) {
     const float u = ldg_stream1(rowp + e);
     float t = u;
     if (c.inv_in) t = __fmul_rn(t, __ldcg(c.inv_in + cbase + col_of(e, c.kk)));
@@ -388,10 +478,10 @@ __device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int
   const int row_len = J * kk;
   const bool use_smem = (J <= kScanCols);
   if (use_smem) {
-    for (int j = threadIdx.x; j < J; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
+    for (int j = ctid(); j < J; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
     cbar();
   }
-  for (int p = threadIdx.x; p < row_len; p += kThreads) {
+  for (int p = ctid(); p < row_len; p += kThreads) {
     float mn = DFQ_INF, mx = -DFQ_INF;
     const float* q = w + (size_t)r0 * row_len + p;
 #pragma unroll 8
@@ -405,11 +495,39 @@ __device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int
   }
   if (use_smem) {
     cbar();
-    for (int j = threadIdx.x; j < J; j += kThreads) {
+    for (int j = ctid(); j < J; j += kThreads) {
       atomic_min_f(dmin + g * gi + j, smin[j]);
       atomic_max_f(dmax + g * gi + j, smax[j]);
     }
     cbar();
+  }
+}
+
+// Column extrema of a pass tile resident in shared memory: rows [row0, row0 + nrows) of a `second` layer (J columns of kk
+// taps per row, `go` rows and `gi` columns per group).  One item = the kk taps of one (row, column).  The partial extrema go
+// to the CTA's shared-memory arrays (`own`: this thread is the only one that ever touches its columns -> plain
+// read-modify-write; otherwise shared-memory atomics), or straight to global atomics when the layer has too many columns.
+__device__ __forceinline__ void scan_tile_smem(const float* __restrict__ buf, int row0, int nrows, int J, int kk, int go, int gi,
+                                               bool single_group, bool own, bool use_smem, float* smin, float* smax, float* dmin, float* dmax) {
+  const int items = nrows * J;
+  for (int idx = ctid(); idx < items; idx += kThreads) {
+    const float* p = buf + (size_t)idx * kk;
+    float mn = p[0], mx = mn;
+    if (kk == 9) {
+#pragma unroll
+      for (int k = 1; k < 9; ++k) { const float v = p[k]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+    } else {
+      for (int k = 1; k < kk; ++k) { const float v = p[k]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+    }
+    int row = 0, j = idx;
+    if (nrows > 1) { row = idx / J; j = idx - row * J; }
+    const int col = single_group ? j : ((row0 + row) / go) * gi + j;
+    if (use_smem) {
+      if (own) { smin[col] = fminf(smin[col], mn); smax[col] = fmaxf(smax[col], mx); }
+      else { atomic_min_f(smin + col, mn); atomic_max_f(smax + col, mx); }
+    } else {
+      atomic_min_f(dmin + col, mn); atomic_max_f(dmax + col, mx);
+    }
   }
 }
 
@@ -432,30 +550,35 @@ __device__ __forceinline__ void scan_layer(float* arena, const DfqLayer* L, cons
 __device__ __forceinline__ void reset_cols(float* arena, const DfqLayer& l, const DfqRelation& r, int buf) {
   float* a = arena + l.cmin_off + (size_t)buf * r.channels;
   float* b = arena + l.cmax_off + (size_t)buf * r.channels;
-  for (int j = threadIdx.x; j < r.channels; j += kThreads) { __stcg(a + j, DFQ_INF); __stcg(b + j, -DFQ_INF); }
+  for (int j = ctid(); j < r.channels; j += kThreads) { __stcg(a + j, DFQ_INF); __stcg(b + j, -DFQ_INF); }
 }
 
 // Walks the pass tiles of this CTA's span in one step, skipping the layers of converged groups.  The producer thread
-// keeps a second copy kPipeStages-1 tiles ahead; both copies see the same `done` flags (they only change at sweep end).
+// keeps a second copy kCleStages-1 tiles ahead; both copies see the same `done` flags (they only change at sweep end).
 struct PassIter {
   const long long* ptr; const int* step_layers; const DfqLayer* L; const GroupState* G;
-  int q, q_begin, q_end;
+  int q, q_end;
+  long long q_lo, q_hi;   // tile range of task q, cached: the per-tile advance touches no global memory
   TileCursor cur;
   int q_live;   // last task whose group was checked and found still iterating (one uncached read per layer, not per tile)
   __device__ __forceinline__ void settle() {
     while (cur.valid()) {
-      while (q + 1 < q_end && ptr[q + 1] <= cur.t) ++q;
+      if (cur.t >= q_hi) {
+        do { ++q; } while (q + 1 < q_end && ptr[q + 1] <= cur.t);
+        q_lo = ptr[q]; q_hi = ptr[q + 1];
+      }
       if (q != q_live) {
-        if (*((volatile const int*)&G[L[step_layers[q]].group].done)) { cur.seek(ptr[q + 1]); continue; }
+        if (*((volatile const int*)&G[L[step_layers[q]].group].done)) { cur.seek(q_hi); continue; }
         q_live = q;
       }
       break;
     }
   }
   __device__ __forceinline__ void start(const long long* p, const int* sl, const DfqLayer* L_, const GroupState* G_, int qb, int qe) {
-    ptr = p; step_layers = sl; L = L_; G = G_; q_begin = qb; q_end = qe; q_live = -1;
+    ptr = p; step_layers = sl; L = L_; G = G_; q_end = qe; q_live = -1;
     cur.init(p[qb], p[qe]);
     q = cur.valid() ? find_task(p, qb, qe, cur.t) : qb;
+    q_lo = p[q]; q_hi = (q < qe) ? p[q + 1] : p[q];
     settle();
   }
   __device__ __forceinline__ bool valid() const { return cur.valid(); }
@@ -466,7 +589,7 @@ struct PassIter {
     const int row_len = l.cols * l.kk;
     const int rpt = pipe_rows_per_tile(row_len);
     d.task = li;
-    d.row0 = (int)(cur.t - ptr[q]) * rpt;
+    d.row0 = (int)(cur.t - q_lo) * rpt;
     d.nrows = min(rpt, l.rows - d.row0);
     d.floats = d.nrows * row_len;
     d.gptr = arena + l.w_off + (size_t)d.row0 * row_len;
@@ -476,7 +599,7 @@ struct PassIter {
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// Warp-specialised pass.  Shared-memory ring of kPipeStages tiles per CTA:
+// Warp-specialised pass.  Shared-memory ring of kCleStages tiles per CTA:
 //   producer warp (lane 0):  for every tile  [expect_tx + cp.async.bulk load] -> prefetch the channel's column extrema into the
 //                            stage mailbox -> arrive(full);  when the consumers hand a tile back (done):  per-channel bookkeeping
 //                            (S, 1/s, bias, BN vectors, derived column extrema) -> cp.async.bulk store -> stage free
@@ -485,147 +608,216 @@ struct PassIter {
 // off their critical path: ONE consumer barrier per tile (the block reduction).
 // ------------------------------------------------------------------------------------------------------------
 struct WsPipe {
-  float* stage[kPipeStages];
-  uint64_t* full;     // [S] producer -> consumers (1 arrival + tx bytes)
-  uint64_t* done;     // [S] consumers -> producer (kThreads arrivals)
-  TileDesc* desc;     // [S]
-  StagePub* pub;      // [S]
+  unsigned char* base;   // everything is derived from it: no pointer arrays (a runtime-indexed array would live in local memory)
+  __device__ __forceinline__ float* stage(int i) const { return (float*)(base + (size_t)i * kStageBytes); }
+  __device__ __forceinline__ uint64_t* full(int i) const { return (uint64_t*)(base + (size_t)kCleStages * kStageBytes) + i; }
+  __device__ __forceinline__ uint64_t* done(int i) const { return (uint64_t*)(base + (size_t)kCleStages * kStageBytes + 128) + i; }
+  __device__ __forceinline__ TileDesc* desc(int i) const { return (TileDesc*)(base + (size_t)kCleStages * kStageBytes + 256) + i; }
+  __device__ __forceinline__ StagePub* pub(int i) const {
+    return (StagePub*)(base + (size_t)kCleStages * kStageBytes + 256 + kCleStages * sizeof(TileDesc)) + i;
+  }
   __device__ void init(unsigned char* smem) {
-    for (int i = 0; i < kPipeStages; ++i) stage[i] = (float*)(smem + (size_t)i * kStageBytes);
-    unsigned char* p = smem + (size_t)kPipeStages * kStageBytes;
-    full = (uint64_t*)p;
-    done = (uint64_t*)(p + 64);
-    desc = (TileDesc*)(p + 128);
-    pub = (StagePub*)(p + 128 + kPipeStages * sizeof(TileDesc));
+    base = smem;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < kPipeStages; ++i) { mbar_init(full + i, 1); mbar_init(done + i, kThreads); }
+      for (int i = 0; i < kCleStages; ++i) { mbar_init(full(i), 1); mbar_init(done(i), kThreads); }
       mbar_fence_init();
     }
     __syncthreads();
   }
   static constexpr size_t smem_bytes() {
-    return (size_t)kPipeStages * kStageBytes + 128 + kPipeStages * (sizeof(TileDesc) + sizeof(StagePub)) + 64;
+    return (size_t)kCleStages * kStageBytes + 256 + kCleStages * (sizeof(TileDesc) + sizeof(StagePub)) + 64;
   }
 };
-static_assert(kPipeStages <= 8, "barrier arrays are 64 bytes");
+static_assert(kCleStages <= 16, "barrier arrays are 128 bytes");
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // Producer WARP: issue / retire the tiles of one step.  `count` = tiles this CTA has moved since kernel start.
-// One iteration retires tile m (consumers are done with it) and issues tile m + kPipeStages into the stage it frees;
-// three lanes work side by side so the iteration costs ONE global-memory latency instead of their sum:
-//   lane 0  bulk store of tile m -> wait until the store has read the stage -> bulk load of the new tile
+// One iteration retires tile m (the consumers no longer need its stage) and issues tile m + kCleStages into that stage;
+// the lanes work side by side so an iteration costs ONE global-memory latency instead of their sum:
+//   lane 0  bulk load of the new tile
 //   lane 1  per-channel bookkeeping of tile m (publish_row: S, 1/s, bias, BN vectors, derived column extrema)
 //   lane 2  prefetch of the new tile's column extrema into its mailbox
-__device__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
-                           unsigned long long& count, const DfqCleParams& P, int sweep, CleCtl* ctl, bool tr) {
+// `scan`: the initial column scan -- tiles are only loaded, no mailbox traffic.
+__device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
+                           unsigned long long& count, const DfqCleParams P, int sweep, CleCtl* ctl, bool tr, bool scan) {
   const int lane = threadIdx.x & 31;
   const unsigned long long count0 = count;
   unsigned long long n = count, m = count;     // next tile to issue / to retire (uniform across the warp)
   RowCtx ctx;                                  // lane 1: layer being retired; lane 2: layer being issued
   int li = -1;
+  int end_pending = kTeams;                    // the TK_END sentinels go last, one per consumer team
+  if (lane == 0) fence_proxy_async_all();      // rows written with plain stores before the last grid barrier -> bulk loads
   for (;;) {
-    const bool room = (n - m) < (unsigned long long)kPipeStages;
-    if (!(pit.valid() && room) && m == n) break;
-    const bool do_retire = !room || !pit.valid();
+    const bool more = pit.valid() || end_pending > 0;
+    const bool room = (n - m) < (unsigned long long)kCleStages;
+    if (!(more && room) && m == n) break;
+    const bool do_retire = !room || !more;
     if (do_retire) {
-      const int sr = (int)(m % kPipeStages);
-      mbar_wait(ws.done + sr, (uint32_t)((m / kPipeStages) & 1));          // the consumers are done with tile m
+      const int sr = (int)(m % kCleStages);
+      mbar_wait(ws.done(sr), (uint32_t)((m / kCleStages) & 1));          // the consumers are done with tile m's stage
+#ifdef DFQ_TILE_TRACE
       if (tr && lane == 0 && m - count0 < 48) ctl->tile_ns[m - count0][4] = gtimer();
-      const TileDesc d = ws.desc[sr];
-      const StagePub pb = ws.pub[sr];
-      __syncwarp();                                                          // everyone holds a copy before the stage is recycled
-      if (lane == 0 && d.kind == TK_BULK) {
-        bulk_s2g(d.gptr, ws.stage[sr], (uint32_t)d.floats * 4u);
-        bulk_commit();
-        bulk_wait_read<0>();                                                 // the stage may be overwritten now
-        if (tr && m - count0 < 48) ctl->tile_ns[m - count0][5] = gtimer();
-      }
-      if (lane == 1 && pb.valid) {
-        if (d.task != li) { make_ctx(ctx, arena, L, R, d.task, sweep); li = d.task; }
-        publish_row(ctx, P, d.row0, pb.s, pb.inv, pb.cmn, pb.cmx);
+#endif
+      if (!scan) {
+        const TileDesc d = *ws.desc(sr);
+        const StagePub pb = *ws.pub(sr);
+        __syncwarp();                                                        // everyone holds a copy before the stage is recycled
+        if (kTmaStore && lane == 0 && d.kind == TK_BULK) {
+          bulk_s2g(d.gptr, ws.stage(sr), (uint32_t)d.floats * 4u);
+          bulk_commit();
+          bulk_wait_read<0>();                                               // the stage may be overwritten now
+        }
+        if (lane == 1 && pb.valid) {
+          if (d.task != li) { make_ctx(ctx, arena, L, R, d.task, sweep); li = d.task; }
+          publish_row(ctx, P, d.row0, pb.s, pb.inv, pb.cmn, pb.cmx);
+        }
       }
       m++;
     }
-    if (pit.valid() && (n - m) < (unsigned long long)kPipeStages) {
+    if (more && (n - m) < (unsigned long long)kCleStages) {
       TileDesc d;
-      pit.fill(d, arena);
-      pit.next();
-      const int si = (int)(n % kPipeStages);
+      if (pit.valid()) { pit.fill(d, arena); pit.next(); }
+      else { d.gptr = nullptr; d.task = -1; d.row0 = d.floats = 0; d.kind = TK_END; d.nrows = --end_pending; }
+      const int si = (int)(n % kCleStages);
       if (lane == 0) {
-        ws.desc[si] = d;
+        *ws.desc(si) = d;
         if (d.kind == TK_BULK) {
-          mbar_expect_tx(ws.full + si, (uint32_t)d.floats * 4u);
-          bulk_g2s(ws.stage[si], d.gptr, (uint32_t)d.floats * 4u, ws.full + si);
+          mbar_expect_tx(ws.full(si), (uint32_t)d.floats * 4u);
+          bulk_g2s(ws.stage(si), d.gptr, (uint32_t)d.floats * 4u, ws.full(si));
         }
+#ifdef DFQ_TILE_TRACE
         if (tr && n - count0 < 48) ctl->tile_ns[n - count0][6] = gtimer();
+#endif
       }
       if (lane == 2) {
         StagePub pb; pb.valid = 0; pb.cmn = pb.cmx = pb.s = pb.inv = 0.f;
-        if (d.nrows == 1 && d.kind != TK_DIRECT) {
+        if (!scan && d.nrows == 1 && (d.kind == TK_BULK || d.kind == TK_PLAIN)) {
           if (d.task != li) { make_ctx(ctx, arena, L, R, d.task, sweep); li = d.task; }
           if (ctx.has_out) { pb.cmn = __ldcg(ctx.cmin_rd + d.row0); pb.cmx = __ldcg(ctx.cmax_rd + d.row0); pb.valid = 1; }
         }
-        ws.pub[si] = pb;
+        *ws.pub(si) = pb;
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(ws.full + si);   // phase completes when this arrival AND the bulk bytes have landed
-        if (tr && n - count0 < 48) ctl->tile_ns[n - count0][7] = gtimer();
-      }
+      if (lane == 0) mbar_arrive(ws.full(si));   // phase completes when this arrival AND the bulk bytes have landed
       n++;
     }
     __syncwarp();
   }
-  if (lane == 0) {
+  if (kTmaStore && lane == 0) {
     bulk_wait_all();
     fence_proxy_async_all();
-    __threadfence();
   }
+  __threadfence();                  // lane 1's bookkeeping stores, before the grid barrier
   __syncwarp();
   count = n;
 }
 
-__global__ void __launch_bounds__(kCtaThreads, kPipeCtas)
+__global__ void __launch_bounds__(kCtaThreads, kCleCtas)
 k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelation* __restrict__ R, int nR,
              const int* __restrict__ step_ptr, const int* __restrict__ step_layers, int n_steps,
              const int* __restrict__ step_rescan, const long long* __restrict__ pass_ptr,
              const long long* __restrict__ scan_ptr, const int* __restrict__ scan_layers, int n_scan,
              DfqCleParams P, CleCtl* ctl, GroupState* G, int nG) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ float red[2 * 2 * 8];
-  __shared__ double dred[8];
-  __shared__ RowCtx sctx;
-  __shared__ __align__(16) float s_inv[kInvCache + 4];   // 1/s of the current layer's input columns
+  // per-team scratch
+  __shared__ float red_all[kTeams][2 * 2 * 8];
+  __shared__ double dred_all[kTeams][8];
+  __shared__ RowCtx sctx_all[kTeams];
+  __shared__ __align__(16) float s_inv_all[kTeams][kInvCache + 4];   // 1/s of the current layer's input columns
+  const int tm = threadIdx.x < kTeams * kThreads ? team() : 0;
+  float* red = red_all[tm];
+  double* dred = dred_all[tm];
+  RowCtx& sctx = sctx_all[tm];
+  float* s_inv = s_inv_all[tm];
   extern __shared__ __align__(128) unsigned char pipe_smem[];
-  // the column-scan scratch aliases the (idle) first pipe stage: scans and passes never overlap
-  float* smin = (float*)pipe_smem;
-  float* smax = smin + kScanCols;
-  static_assert(2 * kScanCols * sizeof(float) <= (size_t)kStageBytes, "scan scratch must fit one stage");
+  // the column-scan scratch aliases the reciprocal-scale cache: scans and passes never overlap
+  float* smin = s_inv;
+  float* smax = s_inv + kScanCols;
+  static_assert(2 * kScanCols <= kInvCache + 4, "scan scratch must fit the reciprocal-scale cache");
   WsPipe ws;
   ws.init(pipe_smem);
-  const bool producer = threadIdx.x >= kThreads;
+  const bool producer = threadIdx.x >= kTeams * kThreads;
   int parity = 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ctid() >> 5, lane = ctid() & 31;
   unsigned long long count = 0;     // tiles moved through the ring so far (advances identically in both roles)
+  // first tile index >= c that belongs to this thread's team
+  auto my_first = [&](unsigned long long c) { return c + (unsigned long long)((tm + kTeams - (int)(c % kTeams)) % kTeams); };
 
   int tmark = 0;
   auto mark = [&]() { if (blockIdx.x == 0 && threadIdx.x == 0 && tmark < 16) ctl->t_ns[tmark] = gtimer(); tmark++; };
   mark();
   // ---- phase 0: column extrema of every `second` layer (buffer 0) -----------------------------
   if (!producer) {
-    for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) G[g].diff = 10.0;   // dfq.py:81
-    for (int li = blockIdx.x; li < nL; li += gridDim.x)
+    for (int g = vblock() * kThreads + ctid(); g < nG; g += vgrid() * kThreads) G[g].diff = 10.0;   // dfq.py:81
+    for (int li = vblock(); li < nL; li += vgrid())
       if (L[li].rel_in >= 0) reset_cols(arena, L[li], R[L[li].rel_in], 0);
   }
   grid.sync();
-  if (!producer) {  // scan_ptr[0 .. n_scan]: tile prefix over scan_layers (all `second` layers)
-    const TileSpan sp = tile_span(scan_ptr, 0, n_scan);
-    for (int q = sp.q; q < n_scan && scan_ptr[q] < sp.hi; ++q) {
-      const long long base = scan_ptr[q];
-      scan_layer(arena, L, R, scan_layers[q], 0, max(sp.lo, base) - base, min(sp.hi, scan_ptr[q + 1]) - base, smin, smax);
+  {  // scan_ptr[0 .. n_scan]: pass-tile prefix over scan_layers (all `second` layers); the tiles stream through the ring
+    if (producer) {
+      PassIter it;
+      it.start(scan_ptr, scan_layers, L, G, 0, n_scan);
+      ws_produce(arena, L, R, it, ws, count, P, 0, ctl, false, true);
+    } else {
+      int cur_li = -1, nch = 0, J = 0, kk = 0, go = 1, gi = 1;
+      bool use_smem = false, own = false, single = true;
+      float *dmin = nullptr, *dmax = nullptr;
+      // fold the CTA's partial extrema of the current layer into the global arrays; leave the scratch reset
+      auto flush = [&]() {
+        if (cur_li < 0 || !use_smem) return;
+        cbar();
+        for (int j = ctid(); j < nch; j += kThreads) {
+          const float mn = smin[j], mx = smax[j];
+          if (mn != DFQ_INF || mx != -DFQ_INF) {
+            atomic_min_f(dmin + j, mn); atomic_max_f(dmax + j, mx);
+            smin[j] = DFQ_INF; smax[j] = -DFQ_INF;
+          }
+        }
+        cbar();
+      };
+      for (int j = ctid(); j < kScanCols; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
+      cbar();
+      for (count = my_first(count);; count += kTeams) {
+        const int sidx = (int)(count % kCleStages);
+        mbar_wait(ws.full(sidx), (uint32_t)((count / kCleStages) & 1));
+        const TileDesc d = *ws.desc(sidx);
+        if (d.kind == TK_END) { mbar_arrive(ws.done(sidx)); count += 1 + d.nrows; break; }   // nrows: sentinels still to come
+        float* buf = ws.stage(sidx);
+        if (d.kind == TK_PLAIN) {
+          for (int i = ctid(); i < d.floats; i += kThreads) buf[i] = ldg_stream1(d.gptr + i);
+          fence_proxy_async_smem();
+          cbar();
+        }
+        if (d.task != cur_li) {
+          flush();
+          cur_li = d.task;
+          const DfqLayer l = L[cur_li];
+          const DfqRelation r = R[l.rel_in];
+          nch = r.channels; J = l.cols; kk = l.kk; go = r.go; gi = r.gi;
+          single = (r.groups == 1);
+          use_smem = (nch <= kScanCols);
+          own = (pipe_rows_per_tile(J * kk) == 1);
+          dmin = arena + l.cmin_off; dmax = arena + l.cmax_off;    // buffer 0
+        }
+        if (d.kind == TK_DIRECT) {   // a row longer than a stage: straight from global memory
+          flush();
+          for (int r = d.row0; r < d.row0 + d.nrows; ++r) {
+            const int g = r / go;
+            scan_cols_tile(arena + L[cur_li].w_off, J, kk, g, gi, r, r + 1, dmin, dmax, smin, smax);
+          }
+          if (J <= kScanCols) {      // scan_cols_tile leaves its scratch dirty
+            for (int j = ctid(); j < J; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
+            cbar();
+          }
+        } else {
+          scan_tile_smem(buf, d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
+        }
+        mbar_arrive(ws.done(sidx));
+      }
+      flush();
     }
   }
   grid.sync();
@@ -634,10 +826,10 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
   for (int sweep = 0;; ++sweep) {
     const int slot = sweep % 3;
     for (int p = 0; p < n_steps; ++p) {
-      PassIter it;
-      it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
       if (producer) {
-        ws_produce(arena, L, R, it, ws, count, P, sweep, ctl, blockIdx.x == 0 && sweep == 0 && p == 0);
+        PassIter it;
+        it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
+        ws_produce(arena, L, R, it, ws, count, P, sweep, ctl, blockIdx.x == 0 && sweep == 0 && p == 0, false);
       } else {
         double dacc = 0.0;
         int cur_g = -1;
@@ -648,7 +840,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
           cbar();
           if (lane == 0) dred[warp] = dacc;
           cbar();
-          if (threadIdx.x == 0) {
+          if (ctid() == 0) {
             double t = 0.0;
 #pragma unroll
             for (int i = 0; i < kWarps; ++i) t += dred[i];
@@ -657,17 +849,24 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
           dacc = 0.0;
         };
         int cur_li = -1, in_mode = IN_NONE;
+#ifdef DFQ_TILE_TRACE
         const bool tr = (blockIdx.x == 0 && threadIdx.x == 0 && sweep == 0 && p == 0);
         int trn = 0;
-        while (it.valid()) {
-          const int sidx = (int)(count % kPipeStages);
-          if (tr && trn < 48) ctl->tile_ns[trn][0] = gtimer();
-          mbar_wait(ws.full + sidx, (uint32_t)((count / kPipeStages) & 1));
-          if (tr && trn < 48) ctl->tile_ns[trn][1] = gtimer();
-          const TileDesc d = ws.desc[sidx];
-          float* buf = ws.stage[sidx];
+#define DFQ_TT(i) do { if (tr && trn < 48) ctl->tile_ns[trn][i] = gtimer(); } while (0)
+#else
+#define DFQ_TT(i) do { } while (0)
+#endif
+        for (count = my_first(count);; count += kTeams) {
+          const int sidx = (int)(count % kCleStages);
+          DFQ_TT(0);
+          mbar_wait(ws.full(sidx), (uint32_t)((count / kCleStages) & 1));
+          DFQ_TT(1);
+          const TileDesc d = *ws.desc(sidx);
+          if (d.kind == TK_END) { mbar_arrive(ws.done(sidx)); count += 1 + d.nrows; break; }
+          float* buf = ws.stage(sidx);
           if (d.kind == TK_PLAIN) {            // a tile the TMA unit cannot move: cooperative fetch
-            for (int i = threadIdx.x; i < d.floats; i += kThreads) buf[i] = ldg_stream1(d.gptr + i);
+            for (int i = ctid(); i < d.floats; i += kThreads) buf[i] = ldg_stream1(d.gptr + i);
+            fence_proxy_async_smem();          // the stage's next refill may be a bulk load (async proxy)
             cbar();
           }
           if (d.task != cur_li) {
@@ -675,7 +874,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
             const int g = L[cur_li].group;
             if (g != cur_g) { flush(); cur_g = g; }
             cbar();                              // everyone is done with the previous layer's context
-            if (threadIdx.x == 0) make_ctx(sctx, arena, L, R, cur_li, sweep);
+            if (ctid() == 0) make_ctx(sctx, arena, L, R, cur_li, sweep);
             cbar();
             if (sctx.inv_in == nullptr) in_mode = IN_NONE;
             else if (sctx.cols == 1) in_mode = IN_UNIFORM;
@@ -683,8 +882,8 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
             else if (sctx.inv_cached && sctx.kk == 9) in_mode = IN_KK9;
             else in_mode = IN_GENERIC;
             if (in_mode == IN_KK1 || in_mode == IN_KK9) {
-              for (int j = threadIdx.x; j < sctx.cols; j += kThreads) s_inv[j] = __ldcg(sctx.inv_in + j);
-              if (threadIdx.x == 0) s_inv[sctx.cols] = 1.f;
+              for (int j = ctid(); j < sctx.cols; j += kThreads) s_inv[j] = __ldcg(sctx.inv_in + j);
+              if (ctid() == 0) s_inv[sctx.cols] = 1.f;
               cbar();
             }
             if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0)
@@ -693,24 +892,31 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
           const RowCtx& c = sctx;
           if (d.kind == TK_DIRECT) {
             for (int r = 0; r < d.nrows; ++r) cle_row_generic(c, P, d.row0 + r, red, parity, dacc);
+            mbar_arrive(ws.done(sidx));
           } else {
-            StagePub* pub = ws.pub + sidx;
-            cle_tile_smem(c, P, in_mode, buf, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr);
+            // rows leave from the consumers' registers (`done` is arrived inside), or in place for the producer's bulk store
+            StagePub* pub = ws.pub(sidx);
+            cle_tile_smem(c, P, in_mode, buf, d.gptr, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr,
+                          ws.done(sidx));
+            if (kTmaStore) {
+              if (d.kind == TK_BULK) {
+                fence_proxy_async_smem();          // my generic-proxy writes -> visible to the bulk store
+              } else {
+                cbar();
+                for (int i = ctid(); i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
+              }
+              mbar_arrive(ws.done(sidx));         // hand the tile back to the producer
+            }
           }
-          if (tr && trn < 48) ctl->tile_ns[trn][2] = gtimer();
-          if (d.kind == TK_BULK) {
-            fence_proxy_async_smem();            // my generic-proxy writes -> visible to the bulk store
-          } else if (d.kind == TK_PLAIN) {
-            cbar();
-            for (int i = threadIdx.x; i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
-          }
-          mbar_arrive(ws.done + sidx);           // hand the tile back to the producer
-          if (tr && trn < 48) ctl->tile_ns[trn][3] = gtimer();
+          DFQ_TT(2);
+#ifdef DFQ_TILE_TRACE
           trn++;
-          count++;
-          it.next();
+#endif
         }
+#undef DFQ_TT
         flush();
+        fence_proxy_async_all();   // this pass's plain row stores -> the next pass's bulk loads (async proxy)
+        __threadfence();
       }
       grid.sync();
       mark();
@@ -722,9 +928,9 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
             if (L[li].col_mode == 2 && L[li].rel_in >= 0 && !*((volatile int*)&G[L[li].group].done)) {
               const DfqRelation r = R[L[li].rel_in];
               const long long nt = scan_tiles(r.groups, r.go);
-              long long first = ((long long)blockIdx.x - sbase) % (long long)gridDim.x;
-              if (first < 0) first += gridDim.x;
-              for (long long t = first; t < nt; t += gridDim.x)
+              long long first = ((long long)vblock() - sbase) % (long long)vgrid();
+              if (first < 0) first += vgrid();
+              for (long long t = first; t < nt; t += vgrid())
                 scan_layer(arena, L, R, li, (sweep & 1) ^ 1, t, t + 1, smin, smax);
               sbase += nt;
             }
@@ -736,7 +942,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
     // ---- exit rule of dfq.py:105-115, one thread per group ------------------------------------------------
     const int n = sweep + 1;
     if (!producer) {
-      for (int g = blockIdx.x * kThreads + threadIdx.x; g < nG; g += gridDim.x * kThreads) {
+      for (int g = vblock() * kThreads + ctid(); g < nG; g += vgrid() * kThreads) {
         GroupState& st = G[g];
         if (st.done) continue;
         const double diff_tmp = st.acc[slot];
@@ -807,7 +1013,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   }
   int64_t scan_total = 0;
   for (int i = 0; i < n_layers; ++i)
-    if (layers[i].rel_in >= 0) scan_total += scan_tiles(rels[layers[i].rel_in].groups, rels[layers[i].rel_in].go);
+    if (layers[i].rel_in >= 0) scan_total += pass_tiles(layers[i]);
   max_tiles = std::max(max_tiles, scan_total);
   for (int p = 0; p < n_steps; ++p) {
     int64_t t = 0;
@@ -843,7 +1049,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   for (int i = 0; i < n_layers; ++i)
     if (layers[i].rel_in >= 0) {
       scan_layers.push_back(i);
-      scan_ptr.push_back(scan_ptr.back() + scan_tiles(rels[layers[i].rel_in].groups, rels[layers[i].rel_in].go));
+      scan_ptr.push_back(scan_ptr.back() + pass_tiles(layers[i]));
     }
   int n_scan = (int)scan_layers.size();
   TablePack tp;
@@ -889,7 +1095,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     for (int i = 1; i < 16 && h.t_ns[i]; ++i) fprintf(stderr, " %.3f", (h.t_ns[i] - h.t_ns[i - 1]) * 1e-6);
     fprintf(stderr, "\n");
     if (getenv("DFQ_TRACE_TILES")) {
-      const unsigned long long t0 = h.tile_ns[0][6];
+      const unsigned long long t0 = h.tile_ns[0][1];
       fprintf(stderr, "tile: C.wait C.ready C.done C.arrived | P.retire P.stored P.loadissued P.fullarrive  (us since first load)\n");
       for (int i = 0; i < 48; ++i) {
         fprintf(stderr, "%3d:", i);

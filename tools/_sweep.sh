@@ -1,5 +1,5 @@
 #!/bin/bash
-for lib in libdfq_sm100 lib_novec lib_nocm lib_both; do
+for lib in ${LIBS:-libdfq_sm100}; do
   echo "== $lib"
-  DFQ_LIB=/root/repo/dfq_b200/$lib.so DFQ_TRACE=1 timeout -k 5 200 python bench.py --steps 3 --layers ${1:-2048} --no-cpu-baseline --no-e2e --no-mbv2 2>&1 | grep -E "phase ms" | tail -1 | cut -c1-300
+  DFQ_LIB=/root/repo/dfq_b200/$lib.so DFQ_TRACE=1 timeout -k 5 200 python bench.py --steps 3 --layers ${1:-2048} --no-cpu-baseline --no-e2e --no-mbv2 2>&1 | grep -E "phase ms|phases_ms" | tail -2 | sed -E 's/.*"phases_ms": (\{[^}]*\}).*/\1/' | cut -c1-300
 done
