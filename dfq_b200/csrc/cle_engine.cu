@@ -90,7 +90,7 @@ struct GroupState {
 struct CleCtl {
   int active[2];   // groups still iterating, double-buffered by sweep parity
   double diffs[64];  // diff_tmp per sweep of group 0
-  unsigned long long t_ns[16];  // %globaltimer at phase boundaries (block 0), printed when DFQ_TRACE is set
+  unsigned long long t_ns[32];  // %globaltimer at phase boundaries (block 0), printed when DFQ_TRACE is set
   int grid, per_sm;
   unsigned long long tile_ns[48][8];  // per-tile timeline of block 0 in the first pass (DFQ_TRACE): consumer 0-3, producer 4-7
 };
@@ -170,39 +170,51 @@ __device__ __forceinline__ void cta_minmax(float& mn, float& mx, float* red, int
 struct StagePub { float cmn, cmx, s, inv; int valid; int pad[3]; };
 
 // The per-channel bookkeeping of dfq.py:62-70 + relation.py:20-24 + the derived column extrema, for ONE channel.
+// All loads are issued before the first store (the stores would otherwise fence the loads one global latency apart).
 __device__ __forceinline__ void publish_row(const RowCtx& c, const DfqCleParams P, int o, float s, float inv, float cmn, float cmx) {
+  const bool acc = !P.apply_only && !c.first_sweep;
+  const float a0 = acc ? __ldcg(c.s_acc + o) : 1.f;
+  const float b0 = __ldcg(c.bias + o);
+  const float w0 = c.bnw ? __ldcg(c.bnw + o) : 0.f;
+  const float w1 = c.bnb ? __ldcg(c.bnb + o) : 0.f;
+  const float o0 = c.own_cmin_wr ? __ldcg(c.own_cmin_wr + o) : 0.f;
+  const float o1 = c.own_cmin_wr ? __ldcg(c.own_cmax_wr + o) : 0.f;
   c.s_step[o] = s;
   __stcg(c.inv_out + o, inv);
-  if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(__ldcg(c.s_acc + o), s);
-  __stcg(c.bias + o, __fmul_rn(__ldcg(c.bias + o), s));
-  if (c.bnw) __stcg(c.bnw + o, __fmul_rn(__ldcg(c.bnw + o), s));
-  if (c.bnb) __stcg(c.bnb + o, __fmul_rn(__ldcg(c.bnb + o), s));
+  if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(a0, s);
+  __stcg(c.bias + o, __fmul_rn(b0, s));
+  if (c.bnw) __stcg(c.bnw + o, __fmul_rn(w0, s));
+  if (c.bnb) __stcg(c.bnb + o, __fmul_rn(w1, s));
   if (c.cmin_wr) {  // derived column extrema of the second layer after its column scaling
     __stcg(c.cmin_wr + o, __fmul_rn(cmn, inv));
     __stcg(c.cmax_wr + o, __fmul_rn(cmx, inv));
   }
   if (c.own_cmin_wr) {  // depthwise middle layer: its single-row column is this row
-    __stcg(c.own_cmin_wr + o, __fmul_rn(__ldcg(c.own_cmin_wr + o), s));
-    __stcg(c.own_cmax_wr + o, __fmul_rn(__ldcg(c.own_cmax_wr + o), s));
+    __stcg(c.own_cmin_wr + o, __fmul_rn(o0, s));
+    __stcg(c.own_cmax_wr + o, __fmul_rn(o1, s));
   }
 }
 
-// All threads of the row's group call this with the reduced row extrema; the leader publishes.
-__device__ __forceinline__ float solve_only(const RowCtx& c, const DfqCleParams P, int o, float mn, float mx, float cmn,
-                                            float cmx, float* inv) {
-  if (P.apply_only) {          // replay a given scale vector (multi-GPU replicas): s = S[o], columns get 1/S[o]
-    const float s = __ldcg(c.s_acc + o);
-    *inv = __frcp_rn(s);
-    return s;
+// What a row needs from global memory, fetched ahead of the row by whoever can hide the latency (producer warp for
+// single-row tiles, one lane per row for a warp's batch of rows).
+struct RowIn {
+  float cmn, cmx;   // column extrema of the second layer for this channel (HAS_OUT)
+  float u;          // the row-uniform input factor (IN_UNIFORM)
+  float s_given;    // apply_only: the scale to replay
+};
+__device__ __forceinline__ RowIn fetch_row_in(const RowCtx& c, const DfqCleParams P, int o, bool uniform) {
+  RowIn in; in.cmn = in.cmx = 0.f; in.u = 1.f; in.s_given = 1.f;
+  if (c.has_out) {
+    in.cmn = __ldcg(c.cmin_rd + o); in.cmx = __ldcg(c.cmax_rd + o);
+    if (P.apply_only) in.s_given = __ldcg(c.s_acc + o);
   }
-  return solve_scale(range_of(mn, mx, P.signed_mode), range_of(cmn, cmx, P.signed_mode), P, inv);
+  if (uniform) in.u = __ldcg(c.inv_in + (o / c.in_go) * c.in_gi);
+  return in;
 }
-__device__ __forceinline__ float solve_and_publish(const RowCtx& c, const DfqCleParams P, int o,
-                                                   float mn, float mx, float cmn, float cmx, bool leader) {
-  float inv;
-  const float s = solve_only(c, P, o, mn, mx, cmn, cmx, &inv);
-  if (leader) publish_row(c, P, o, s, inv, cmn, cmx);
-  return s;
+// dfq.py:58-59 + :73 for one channel from its row / column extrema (or the replayed scale)
+__device__ __forceinline__ float solve_row(const DfqCleParams P, const RowIn& in, float mn, float mx, float* inv) {
+  if (P.apply_only) { *inv = __frcp_rn(in.s_given); return in.s_given; }
+  return solve_scale(range_of(mn, mx, P.signed_mode), range_of(in.cmn, in.cmx, P.signed_mode), P, inv);
 }
 
 // How the reciprocal scales of the in-relation map onto the elements of a row (decided once per layer):
@@ -249,18 +261,21 @@ constexpr int kRowRegs = (kStageFloats / 4 + kThreads - 1) / kThreads;
 #define DFQ_TMA_STORE 1
 #endif
 constexpr bool kTmaStore = DFQ_TMA_STORE != 0;
+constexpr size_t kTableCacheBytes = 9 * 1024;   // descriptor tables of a model this small are mirrored in shared memory
 constexpr int TK_END = 3;   // sentinel tile: the pass is over for this CTA (the consumers keep no iterator of their own)
 static_assert(kThreads * kRowRegs * 4 >= kStageFloats, "a single-row tile must fit the consumers' registers");
 
-// One row resident in shared memory (read-only here): [range reduction -> s] (HAS_OUT), rescale, accumulate |new - old|,
-// and write the new row STRAIGHT to global memory.  The stage is read ONCE when the row fits the registers (always for the
-// CTA-wide single-row tiles): shared-memory bandwidth, not HBM, was the limit when the row was re-read and written back
-// for a bulk store (5 shared-memory touches per HBM byte; now 2).  `done`: the stage's consumer->producer barrier, arrived
-// as soon as this thread no longer needs the stage (nullptr: the caller arrives).
+// One row resident in shared memory: [range reduction -> s] (HAS_OUT), rescale, accumulate |new - old|.  The rescaled row goes
+// back into its stage for the producer's bulk store (default), or straight to global memory (DFQ_TMA_STORE=0).  A row with a
+// reduction is read from shared memory ONCE when it fits the registers (always for the CTA-wide single-row tiles).
+// `in`: what the row needs from global memory, fetched ahead by the caller; the scale pair comes back in *s_out / *inv_out
+// and the caller does (or delegates) the per-channel bookkeeping.  `done`: the stage's consumer->producer barrier, arrived as
+// soon as this thread no longer needs the stage (nullptr: the caller arrives).
 template <int TPR, int MODE, bool HAS_OUT>
 __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams P, float* __restrict__ row,
                                              float* __restrict__ grow, int o, int lane, const float* __restrict__ s_inv,
-                                             float* red, int& parity, double& dacc, StagePub* pub, uint64_t* done) {
+                                             float* red, int& parity, double& dacc, const RowIn& in, float* s_out,
+                                             float* inv_out, uint64_t* done) {
   const int n = c.row_len, kk = c.kk;
   const bool vec = ((n & 3) == 0) && (kTmaStore || (((uintptr_t)grow) & 15) == 0);
   auto put4 = [&](int i4, const float4& t) { if (kTmaStore) ((float4*)row)[i4] = t; else stg_stream((float4*)grow + i4, t); };
@@ -268,26 +283,16 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
   const int n4 = n >> 2;
   const double inv_n = c.inv_n;
   const float* inv = nullptr;
-  float u = 1.f;
-  if (MODE == IN_UNIFORM) u = __ldcg(c.inv_in + (o / c.in_go) * c.in_gi);
-  else if (MODE == IN_KK1 || MODE == IN_KK9) inv = s_inv;
+  const float u = in.u;
+  if (MODE == IN_KK1 || MODE == IN_KK9) inv = s_inv;
   else if (MODE == IN_GENERIC) inv = c.inv_in + (o / c.in_go) * c.in_gi;
-  float s = 1.f, cmn = 0.f, cmx = 0.f;
-  if (HAS_OUT) {
-    if (pub) { cmn = pub->cmn; cmx = pub->cmx; }                             // prefetched by the producer warp
-    else { cmn = __ldcg(c.cmin_rd + o); cmx = __ldcg(c.cmax_rd + o); }       // in flight during the reduction
-  }
-  // s from the reduced row extrema; single-row tiles leave the bookkeeping to the producer warp (mailbox)
+  float s = 1.f;
   auto solve = [&](float mn, float mx) {
     if (TPR == 32) { mn = warp_min(mn); mx = warp_max(mx); }
     else cta_minmax(mn, mx, red, parity);
-    if (pub) {
-      float iv;
-      s = solve_only(c, P, o, mn, mx, cmn, cmx, &iv);
-      if (lane == 0) { pub->s = s; pub->inv = iv; }
-    } else {
-      s = solve_and_publish(c, P, o, mn, mx, cmn, cmx, lane == 0);
-    }
+    float iv;
+    s = solve_row(P, in, mn, mx, &iv);
+    *s_out = s; *inv_out = iv;
   };
   float dsum = 0.f;
   // a row that only gets its columns scaled (no reduction to wait for) streams through the in-place loop further down when
@@ -368,21 +373,52 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
   dacc += (double)dsum * inv_n;
 }
 
-// A tile of whole rows in shared memory -> rescaled rows (in global memory at `g`, or in place for the bulk store);
-// every consumer thread arrives on `done` exactly once.
+// A tile of whole rows in shared memory -> rescaled rows (in place for the bulk store, or in global memory at `g`);
+// with DFQ_TMA_STORE=0 every consumer thread arrives on `done` in here.
+//   one row   : the whole team works on it; its global-memory inputs arrive in the stage mailbox and the bookkeeping is left
+//               to the producer warp (mailbox again)
+//   many rows : a warp per row, 32 rows per batch -- lane j fetches row j's inputs before the batch and does row j's
+//               bookkeeping after it, so a batch pays TWO global-memory latencies instead of two per row
 template <int MODE, bool HAS_OUT>
 __device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams P, float* buf, float* g, int row0,
                                               int nrows, const float* s_inv, float* red, int& parity, double& dacc,
                                               StagePub* pub, uint64_t* done) {
   const int warp = ctid() >> 5, lane = ctid() & 31;
   if (nrows == 1) {
-    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, g, row0, ctid(), s_inv, red, parity, dacc, HAS_OUT ? pub : nullptr,
+    RowIn in;
+    if (HAS_OUT && pub) { in.cmn = pub->cmn; in.cmx = pub->cmx; in.u = 1.f; in.s_given = 1.f;
+                          if (MODE == IN_UNIFORM) in.u = __ldcg(c.inv_in + (row0 / c.in_go) * c.in_gi);
+                          if (P.apply_only) in.s_given = __ldcg(c.s_acc + row0); }
+    else in = fetch_row_in(c, P, row0, MODE == IN_UNIFORM);
+    float sv = 1.f, iv = 1.f;
+    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, g, row0, ctid(), s_inv, red, parity, dacc, in, &sv, &iv,
                                           kTmaStore ? nullptr : done);
+    if (HAS_OUT && ctid() == 0) {
+      if (pub) { pub->s = sv; pub->inv = iv; }
+      else publish_row(c, P, row0, sv, iv, in.cmn, in.cmx);
+    }
   } else {
     const int row_len = c.row_len;
-    for (int r = warp; r < nrows; r += kWarps)
-      cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, g + (size_t)r * row_len, row0 + r, lane, s_inv, red,
-                                      parity, dacc, nullptr, nullptr);
+    const int mine = (nrows - warp + kWarps - 1) / kWarps;       // this warp's rows: warp, warp + kWarps, ...
+    for (int base = 0; base < mine; base += 32) {
+      const int il = base + lane;
+      const int ol = row0 + warp + il * kWarps;
+      RowIn mine_in; mine_in.cmn = mine_in.cmx = 0.f; mine_in.u = 1.f; mine_in.s_given = 1.f;
+      if (il < mine) mine_in = fetch_row_in(c, P, ol, MODE == IN_UNIFORM);
+      float ks = 1.f, kinv = 1.f;
+      const int nb = min(32, mine - base);
+      for (int j = 0; j < nb; ++j) {
+        const int r = warp + (base + j) * kWarps;
+        RowIn in;
+        in.cmn = __shfl_sync(0xffffffffu, mine_in.cmn, j); in.cmx = __shfl_sync(0xffffffffu, mine_in.cmx, j);
+        in.u = __shfl_sync(0xffffffffu, mine_in.u, j); in.s_given = __shfl_sync(0xffffffffu, mine_in.s_given, j);
+        float sv = 1.f, iv = 1.f;
+        cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, g + (size_t)r * row_len, row0 + r, lane, s_inv, red,
+                                        parity, dacc, in, &sv, &iv, nullptr);
+        if (lane == j) { ks = sv; kinv = iv; }
+      }
+      if (HAS_OUT && il < mine) publish_row(c, P, ol, ks, kinv, mine_in.cmn, mine_in.cmx);
+    }
     if (!kTmaStore) mbar_arrive(done);
   }
 }
@@ -417,7 +453,10 @@ __device__ __forceinline__ void cle_row_generic(const RowCtx& c, const DfqClePar
       mn = fminf(mn, t); mx = fmaxf(mx, t);
     }
     cta_minmax(mn, mx, red, parity);
-    s = solve_and_publish(c, P, o, mn, mx, __ldcg(c.cmin_rd + o), __ldcg(c.cmax_rd + o), ctid() == 0);
+    RowIn in = fetch_row_in(c, P, o, false);
+    float iv;
+    s = solve_row(P, in, mn, mx, &iv);
+    if (ctid() == 0) publish_row(c, P, o, s, iv, in.cmn, in.cmx);
   }
   float dsum = 0.f;
   for (int e = ctid(); e < c.row_len; e += kThreads) {
@@ -624,7 +663,7 @@ struct WsPipe {
     }
     __syncthreads();
   }
-  static constexpr size_t smem_bytes() {
+  __host__ __device__ static constexpr size_t smem_bytes() {
     return (size_t)kCleStages * kStageBytes + 256 + kCleStages * (sizeof(TileDesc) + sizeof(StagePub)) + 64;
   }
 };
@@ -716,11 +755,11 @@ __device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, cons
 }
 
 __global__ void __launch_bounds__(kCtaThreads, kCleCtas)
-k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelation* __restrict__ R, int nR,
-             const int* __restrict__ step_ptr, const int* __restrict__ step_layers, int n_steps,
-             const int* __restrict__ step_rescan, const long long* __restrict__ pass_ptr,
-             const long long* __restrict__ scan_ptr, const int* __restrict__ scan_layers, int n_scan,
-             DfqCleParams P, CleCtl* ctl, GroupState* G, int nG) {
+k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int nR,
+             const int* step_ptr, const int* step_layers, int n_steps,
+             const int* step_rescan, const long long* pass_ptr,
+             const long long* scan_ptr, const int* scan_layers, int n_scan,
+             DfqCleParams P, CleCtl* ctl, GroupState* G, int nG, const unsigned char* tbl, int tbl_bytes) {
   cg::grid_group grid = cg::this_grid();
   // per-team scratch
   __shared__ float red_all[kTeams][2 * 2 * 8];
@@ -739,6 +778,18 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
   static_assert(2 * kScanCols <= kInvCache + 4, "scan scratch must fit the reciprocal-scale cache");
   WsPipe ws;
   ws.init(pipe_smem);
+  // A small model is latency-bound: every phase walks the descriptor tables with dependent loads.  When the whole table pack
+  // fits (the host decides, tbl_bytes > 0) it is copied into shared memory once and every table pointer is moved onto the copy.
+  if (tbl_bytes > 0) {
+    unsigned char* cache = pipe_smem + ((WsPipe::smem_bytes() + 255) & ~(size_t)255);
+    for (int i = threadIdx.x * 16; i < tbl_bytes; i += kCtaThreads * 16) *(int4*)(cache + i) = *(const int4*)(tbl + i);
+    __syncthreads();
+    // (derive the new pointers from `cache`, not from the kernel arguments: those are assumed to point to global memory)
+#define DFQ_MOVE(ptr) ptr = (decltype(ptr))(cache + ((const unsigned char*)(ptr) - tbl))
+    DFQ_MOVE(L); DFQ_MOVE(R); DFQ_MOVE(step_ptr); DFQ_MOVE(step_layers); DFQ_MOVE(step_rescan); DFQ_MOVE(pass_ptr);
+    DFQ_MOVE(scan_ptr); DFQ_MOVE(scan_layers);
+#undef DFQ_MOVE
+  }
   const bool producer = threadIdx.x >= kTeams * kThreads;
   int parity = 0;
   const int warp = ctid() >> 5, lane = ctid() & 31;
@@ -747,7 +798,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
   auto my_first = [&](unsigned long long c) { return c + (unsigned long long)((tm + kTeams - (int)(c % kTeams)) % kTeams); };
 
   int tmark = 0;
-  auto mark = [&]() { if (blockIdx.x == 0 && threadIdx.x == 0 && tmark < 16) ctl->t_ns[tmark] = gtimer(); tmark++; };
+  auto mark = [&]() { if (blockIdx.x == 0 && threadIdx.x == 0 && tmark < 32) ctl->t_ns[tmark] = gtimer(); tmark++; };
   mark();
   // ---- phase 0: column extrema of every `second` layer (buffer 0) -----------------------------
   if (!producer) {
@@ -937,6 +988,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRela
           }
         }
         grid.sync();
+        mark();
       }
     }
     // ---- exit rule of dfq.py:105-115, one thread per group ------------------------------------------------
@@ -1034,11 +1086,23 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   DFQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DFQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) { set_error("device does not support cooperative launch"); return DFQ_E_NOT_COOPERATIVE; }
-  const size_t dyn_smem = WsPipe::smem_bytes();
+  // table cache for small models (see the kernel): decided before the occupancy query because it adds shared memory
+  const int n_entries_early = step_ptr[n_steps];
+  size_t tbl_est = 0;
+  {
+    int n_scan_est = 0;
+    for (int i = 0; i < n_layers; ++i) n_scan_est += layers[i].rel_in >= 0;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    tbl_est = al(sizeof(DfqLayer) * n_layers) + al(sizeof(DfqRelation) * n_rels) + al(4 * (n_steps + 1)) + al(4 * n_entries_early) +
+              al(4 * n_steps) + al(8 * (n_entries_early + 1)) + al(8 * (n_scan_est + 1)) + al(4 * n_scan_est);
+  }
+  const bool cache_tables = tbl_est <= kTableCacheBytes;
+  const size_t dyn_smem = cache_tables ? ((WsPipe::smem_bytes() + 255) & ~(size_t)255) + tbl_est : WsPipe::smem_bytes();
   DFQ_CUDA(cudaFuncSetAttribute(k_cle_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cle_engine, kCtaThreads, dyn_smem));
   if (per_sm < 1) { set_error("persistent kernel does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
-  const int grid = (int)std::min<int64_t>((int64_t)sms * per_sm, max_tiles);
+  int grid = (int)std::min<int64_t>((int64_t)sms * per_sm, max_tiles);
+  if (const char* e = getenv("DFQ_CLE_GRID")) grid = std::max(1, std::min(grid, atoi(e)));   // experiments: cap the grid
 
   h_occ = ms_since(h0);
   const int n_entries = step_ptr[n_steps];
@@ -1070,8 +1134,11 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   DFQ_CUDA(cudaMemsetAsync(dG, 0, sizeof(GroupState) * n_groups, st));
   h_upload = ms_since(h0);
   DfqCleParams P = *params;
+  const unsigned char* d_tbl = tp.dev;
+  int tbl_bytes = cache_tables ? (int)tp.total : 0;
+  if (cache_tables && tp.total != tbl_est) { set_error("internal: table pack size mismatch"); return DFQ_E_ARG; }
   void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS,
-                  &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups};
+                  &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups, &d_tbl, &tbl_bytes};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kCtaThreads), args, dyn_smem, st));
   h_launch = ms_since(h0);
   CleCtl h;
@@ -1092,7 +1159,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     fprintf(stderr, "[dfq_cle_run] host ms: validate %.3f occupancy %.3f upload %.3f launch %.3f done %.3f\n", h_valid, h_occ,
             h_upload, h_launch, ms_since(h0));
     fprintf(stderr, "[dfq_cle_run] grid %d (%d CTAs/SM) sweeps %d; phase ms:", grid, per_sm, result->n_sweeps);
-    for (int i = 1; i < 16 && h.t_ns[i]; ++i) fprintf(stderr, " %.3f", (h.t_ns[i] - h.t_ns[i - 1]) * 1e-6);
+    for (int i = 1; i < 32 && h.t_ns[i]; ++i) fprintf(stderr, " %.3f", (h.t_ns[i] - h.t_ns[i - 1]) * 1e-6);
     fprintf(stderr, "\n");
     if (getenv("DFQ_TRACE_TILES")) {
       const unsigned long long t0 = h.tile_ns[0][1];

@@ -154,21 +154,27 @@ constexpr long long kTileBlock = DFQ_TILE_BLOCK;
 struct TileCursor {
   long long first, end;     // tiles of the phase
   long long t, blk_end;     // current tile, end of the current block
+  long long B;              // tiles per block: kTileBlock for a large phase, down to 1 so that a small phase still reaches every CTA
   __device__ __forceinline__ void seek(long long tmin) {   // first tile >= tmin owned by this CTA
     const long long G = gridDim.x, b = blockIdx.x;
     if (tmin < first) tmin = first;
-    const long long blk = (tmin - first) / kTileBlock;
+    const long long blk = (tmin - first) / B;
     const long long j = blk / G, r = blk % G;
     long long start_blk;
-    if (r == b) { t = tmin; blk_end = first + (blk + 1) * kTileBlock; return; }
+    if (r == b) { t = tmin; blk_end = first + (blk + 1) * B; return; }
     start_blk = (r < b) ? j * G + b : (j + 1) * G + b;
-    t = first + start_blk * kTileBlock;
-    blk_end = t + kTileBlock;
+    t = first + start_blk * B;
+    blk_end = t + B;
   }
-  __device__ __forceinline__ void init(long long first_, long long end_) { first = first_; end = end_; seek(first_); }
+  __device__ __forceinline__ void init(long long first_, long long end_) {
+    first = first_; end = end_;
+    const long long per_cta = (end_ - first_) / ((long long)gridDim.x * 4);
+    B = per_cta < 1 ? 1 : (per_cta > kTileBlock ? kTileBlock : per_cta);
+    seek(first_);
+  }
   __device__ __forceinline__ bool valid() const { return t < end; }
   __device__ __forceinline__ void next() {
-    if (++t == blk_end) { t += (long long)(gridDim.x - 1) * kTileBlock; blk_end = t + kTileBlock; }
+    if (++t == blk_end) { t += (long long)(gridDim.x - 1) * B; blk_end = t + B; }
   }
 };
 // largest q in [q_begin, q_end) with ptr[q] <= t

@@ -387,17 +387,30 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
           if (b.next_bn_b_off >= 0) __stcg(arena + b.next_bn_b_off + o, __fadd_rn(old_next, -dl));   // dfq.py:204-206,293
         }
       } else {
-        for (int r = warp; r < d.nrows; r += kWarps) {
-          const int o = d.row0 + r;
-          const float* row = pipe.stage[sidx] + (size_t)r * row_len;
-          const float* ex = (ex_cached ? s_ex : arena + b.expect_off) + (size_t)(o / so) * l.cols;
-          const double acc = raw ? bc_row<32, true>(row, l.cols, l.kk, ex, q, lane) : bc_row<32, false>(row, l.cols, l.kk, ex, q, lane);
-          if (lane == 0) {
-            const float dl = (float)acc;
-            __stcg(arena + b.delta_off + o, dl);
-            __stcg(arena + l.bias_off + o, __fadd_rn(__ldcg(arena + l.bias_off + o), (b.flags & 2) ? dl : -dl));
-            if (b.next_bn_b_off >= 0)
-              __stcg(arena + b.next_bn_b_off + o, __fadd_rn(__ldcg(arena + b.next_bn_b_off + o), -dl));
+        // a warp per row, 32 rows per batch: lane j requests row j's read-modify-write operands before the batch and
+        // writes row j's results after it (two global-memory latencies per batch instead of two per row)
+        const int mine = (d.nrows - warp + kWarps - 1) / kWarps;
+        for (int base = 0; base < mine; base += 32) {
+          const int il = base + lane;
+          const int ol = d.row0 + warp + il * kWarps;
+          float old_bias = 0.f, old_next = 0.f, dl = 0.f;
+          if (il < mine) {
+            old_bias = __ldcg(arena + l.bias_off + ol);
+            if (b.next_bn_b_off >= 0) old_next = __ldcg(arena + b.next_bn_b_off + ol);
+          }
+          const int nb = min(32, mine - base);
+          for (int j = 0; j < nb; ++j) {
+            const int r = warp + (base + j) * kWarps;
+            const int o = d.row0 + r;
+            const float* row = pipe.stage[sidx] + (size_t)r * row_len;
+            const float* ex = (ex_cached ? s_ex : arena + b.expect_off) + (size_t)(o / so) * l.cols;
+            const double acc = raw ? bc_row<32, true>(row, l.cols, l.kk, ex, q, lane) : bc_row<32, false>(row, l.cols, l.kk, ex, q, lane);
+            if (lane == j) dl = (float)acc;
+          }
+          if (il < mine) {
+            __stcg(arena + b.delta_off + ol, dl);
+            __stcg(arena + l.bias_off + ol, __fadd_rn(old_bias, (b.flags & 2) ? dl : -dl));              // dfq.py:292 / :164
+            if (b.next_bn_b_off >= 0) __stcg(arena + b.next_bn_b_off + ol, __fadd_rn(old_next, -dl));   // dfq.py:204-206,293
           }
         }
       }
