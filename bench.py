@@ -279,9 +279,9 @@ def run_b200(args, rank, world, local_rank):
         ev[0].record()
         sess.run_bn_fold(stack.fold_plan)
         ev[1].record()
-        res = sess.run_cle_plan(stack.cle_plan)
+        res = sess.run_cle_plan(stack.cle_plan, cols_ready=stack.fold_plan["scanned"])
         ev[2].record()
-        sess.run_bias_correct_plan(stack.bc_plan, 8)
+        sess.run_bias_correct_plan(stack.bc_plan, 8, col_hints=sess.cle_col_hints(stack.cle_plan, res))
         if stack.quant_plan is not None:
             sess.run_quantize(stack.quant_plan)
         ev[3].record()

@@ -17,6 +17,9 @@ LIB_PATH = os.environ.get("DFQ_LIB") or os.path.join(_HERE, "libdfq_sm100.so")  
 ABI_VERSION = 1
 
 
+LAYER_COLS_READY = 1   # DfqLayer.flags
+
+
 class DfqError(RuntimeError):
     pass
 
@@ -25,7 +28,7 @@ class DfqError(RuntimeError):
 LAYER_DT = np.dtype([
     ("w_off", np.int64), ("bias_off", np.int64),
     ("rows", np.int32), ("cols", np.int32), ("kk", np.int32),
-    ("rel_in", np.int32), ("rel_out", np.int32), ("col_mode", np.int32), ("group", np.int32), ("_pad", np.int32),
+    ("rel_in", np.int32), ("rel_out", np.int32), ("col_mode", np.int32), ("group", np.int32), ("flags", np.int32),
     ("cmin_off", np.int64), ("cmax_off", np.int64),
 ], align=True)
 
@@ -52,6 +55,7 @@ FOLD_DT = np.dtype([
     ("layer", np.int32), ("bn_eps", np.float32),
     ("gamma_off", np.int64), ("beta_off", np.int64), ("mean_off", np.int64), ("var_off", np.int64),
     ("fake_w_off", np.int64), ("fake_b_off", np.int64),
+    ("scan_go", np.int32), ("scan_gi", np.int32),
 ], align=True)
 
 TERM_DT = np.dtype([
@@ -63,6 +67,7 @@ BC_LAYER_DT = np.dtype([
     ("layer", np.int32), ("signed_mode", np.int32), ("term_begin", np.int32), ("term_end", np.int32),
     ("expect_len", np.int32), ("flags", np.int32),
     ("expect_off", np.int64), ("delta_off", np.int64), ("next_bn_b_off", np.int64), ("minmax_off", np.int64),
+    ("colmin_off", np.int64), ("colmax_off", np.int64), ("n_col", np.int32), ("_pad", np.int32),
 ], align=True)
 
 QUANT_TASK_DT = np.dtype([
@@ -73,8 +78,8 @@ QUANT_TASK_DT = np.dtype([
 # sizes the C side uses (checked in tests against sizeof via the header's layout rules)
 EXPECTED_SIZES = {
     "DfqLayer": (LAYER_DT, 64), "DfqRelation": (RELATION_DT, 64), "DfqCleParams": (CLE_PARAMS_DT, 48),
-    "DfqCleResult": (CLE_RESULT_DT, 528), "DfqFold": (FOLD_DT, 56), "DfqExpectTerm": (TERM_DT, 32),
-    "DfqBcLayer": (BC_LAYER_DT, 56), "DfqQuantTask": (QUANT_TASK_DT, 32),
+    "DfqCleResult": (CLE_RESULT_DT, 528), "DfqFold": (FOLD_DT, 64), "DfqExpectTerm": (TERM_DT, 32),
+    "DfqBcLayer": (BC_LAYER_DT, 80), "DfqQuantTask": (QUANT_TASK_DT, 32),
 }
 
 _PF = C.c_void_p   # device float*

@@ -80,6 +80,8 @@ class GraphCalibration:
                 v = self._bn[bn_key]
                 table.append((self._layer[a], self._layer[b], v["fake_w"], v["fake_b"]))
             self._cle_plan = sess.plan_cle(table) if table else None
+            # the fold that precedes an equalization also fills the column extrema the equalization starts from
+            self._fold_plan_scan = sess.plan_bn_fold(folds, cle_plan=self._cle_plan) if (folds and self._cle_plan) else None
             # ---- bias correction plan ----------------------------------------------------------------------------------
             items = []
             for step in bias_correction_recipe(graph, bottoms, self.targ_type, bn_type):
@@ -100,16 +102,21 @@ class GraphCalibration:
     def run_device(self, equalize=True, correction=True, quantize_bits: Optional[Tuple[int, int]] = None, signed=False,
                    s_range=(1e-8, 1e8), converge_thres=2e-7, converge_count=20, eps=0):
         sess = self.sess
+        run_cle = equalize and self._cle_plan is not None
+        scan = run_cle and self._fold_plan_scan is not None
         if self._fold_plan is not None:
-            sess.run_bn_fold(self._fold_plan)
-        if equalize and self._cle_plan is not None:
-            self.last_cle = sess.run_cle_plan(self._cle_plan, s_range, converge_thres, converge_count, signed, eps)
+            sess.run_bn_fold(self._fold_plan_scan if scan else self._fold_plan)
+        hints = None
+        if run_cle:
+            self.last_cle = sess.run_cle_plan(self._cle_plan, s_range, converge_thres, converge_count, signed, eps,
+                                              cols_ready=self._fold_plan_scan["scanned"] if scan else None)
+            hints = sess.cle_col_hints(self._cle_plan, self.last_cle)   # weights stay untouched until the correction
         if correction and self._bc_plan is not None:
             if signed:
                 for it in self._bc_items:
                     it["signed"] = True
                 self._bc_plan = sess.plan_bias_correct(self._bc_items)
-            sess.run_bias_correct_plan(self._bc_plan, 8)          # quirk Q2: always 8 bits (dfq.py:218)
+            sess.run_bias_correct_plan(self._bc_plan, 8, col_hints=hints)          # quirk Q2: always 8 bits (dfq.py:218)
         if quantize_bits is not None:
             if self._quant_plan is None or self._quant_bits != tuple(quantize_bits):
                 bw, bb = quantize_bits

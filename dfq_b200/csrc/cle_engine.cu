@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "rowpipe.cuh"
+#include "colscan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -542,34 +543,6 @@ __device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int
   }
 }
 
-// Column extrema of a pass tile resident in shared memory: rows [row0, row0 + nrows) of a `second` layer (J columns of kk
-// taps per row, `go` rows and `gi` columns per group).  One item = the kk taps of one (row, column).  The partial extrema go
-// to the CTA's shared-memory arrays (`own`: this thread is the only one that ever touches its columns -> plain
-// read-modify-write; otherwise shared-memory atomics), or straight to global atomics when the layer has too many columns.
-__device__ __forceinline__ void scan_tile_smem(const float* __restrict__ buf, int row0, int nrows, int J, int kk, int go, int gi,
-                                               bool single_group, bool own, bool use_smem, float* smin, float* smax, float* dmin, float* dmax) {
-  const int items = nrows * J;
-  for (int idx = ctid(); idx < items; idx += kThreads) {
-    const float* p = buf + (size_t)idx * kk;
-    float mn = p[0], mx = mn;
-    if (kk == 9) {
-#pragma unroll
-      for (int k = 1; k < 9; ++k) { const float v = p[k]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
-    } else {
-      for (int k = 1; k < kk; ++k) { const float v = p[k]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
-    }
-    int row = 0, j = idx;
-    if (nrows > 1) { row = idx / J; j = idx - row * J; }
-    const int col = single_group ? j : ((row0 + row) / go) * gi + j;
-    if (use_smem) {
-      if (own) { smin[col] = fminf(smin[col], mn); smax[col] = fmaxf(smax[col], mx); }
-      else { atomic_min_f(smin + col, mn); atomic_max_f(smax + col, mx); }
-    } else {
-      atomic_min_f(dmin + col, mn); atomic_max_f(dmax + col, mx);
-    }
-  }
-}
-
 // scan tiles [t0, t1) of layer li (tile = 32 rows of one group)
 __device__ __forceinline__ void scan_layer(float* arena, const DfqLayer* L, const DfqRelation* R, int li,
                                            int buf, long long t0, long long t1, float* smin, float* smax) {
@@ -804,7 +777,7 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
   if (!producer) {
     for (int g = vblock() * kThreads + ctid(); g < nG; g += vgrid() * kThreads) G[g].diff = 10.0;   // dfq.py:81
     for (int li = vblock(); li < nL; li += vgrid())
-      if (L[li].rel_in >= 0) reset_cols(arena, L[li], R[L[li].rel_in], 0);
+      if (L[li].rel_in >= 0 && !(L[li].flags & DFQ_LAYER_COLS_READY)) reset_cols(arena, L[li], R[L[li].rel_in], 0);
   }
   grid.sync();
   {  // scan_ptr[0 .. n_scan]: pass-tile prefix over scan_layers (all `second` layers); the tiles stream through the ring
@@ -820,13 +793,7 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
       auto flush = [&]() {
         if (cur_li < 0 || !use_smem) return;
         cbar();
-        for (int j = ctid(); j < nch; j += kThreads) {
-          const float mn = smin[j], mx = smax[j];
-          if (mn != DFQ_INF || mx != -DFQ_INF) {
-            atomic_min_f(dmin + j, mn); atomic_max_f(dmax + j, mx);
-            smin[j] = DFQ_INF; smax[j] = -DFQ_INF;
-          }
-        }
+        colscan_flush<kThreads>(ctid(), nch, smin, smax, dmin, dmax);
         cbar();
       };
       for (int j = ctid(); j < kScanCols; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
@@ -864,7 +831,7 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
             cbar();
           }
         } else {
-          scan_tile_smem(buf, d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
+          colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
         }
         mbar_arrive(ws.done(sidx));
       }
@@ -1065,7 +1032,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   }
   int64_t scan_total = 0;
   for (int i = 0; i < n_layers; ++i)
-    if (layers[i].rel_in >= 0) scan_total += pass_tiles(layers[i]);
+    if (layers[i].rel_in >= 0 && !(layers[i].flags & DFQ_LAYER_COLS_READY)) scan_total += pass_tiles(layers[i]);
   max_tiles = std::max(max_tiles, scan_total);
   for (int p = 0; p < n_steps; ++p) {
     int64_t t = 0;
@@ -1091,7 +1058,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   size_t tbl_est = 0;
   {
     int n_scan_est = 0;
-    for (int i = 0; i < n_layers; ++i) n_scan_est += layers[i].rel_in >= 0;
+    for (int i = 0; i < n_layers; ++i) n_scan_est += (layers[i].rel_in >= 0 && !(layers[i].flags & DFQ_LAYER_COLS_READY));
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     tbl_est = al(sizeof(DfqLayer) * n_layers) + al(sizeof(DfqRelation) * n_rels) + al(4 * (n_steps + 1)) + al(4 * n_entries_early) +
               al(4 * n_steps) + al(8 * (n_entries_early + 1)) + al(8 * (n_scan_est + 1)) + al(4 * n_scan_est);
@@ -1111,7 +1078,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   std::vector<int32_t> scan_layers;
   std::vector<long long> scan_ptr(1, 0);
   for (int i = 0; i < n_layers; ++i)
-    if (layers[i].rel_in >= 0) {
+    if (layers[i].rel_in >= 0 && !(layers[i].flags & DFQ_LAYER_COLS_READY)) {   // the others arrive with buffer 0 filled
       scan_layers.push_back(i);
       scan_ptr.push_back(scan_ptr.back() + pass_tiles(layers[i]));
     }

@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "rowpipe.cuh"
+#include "colscan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -69,10 +70,24 @@ __device__ __forceinline__ void fold_row(float* arena, const DfqLayer& l, const 
   }
 }
 
+constexpr int kFoldScanCols = 1024;   // columns whose extrema a CTA accumulates in shared memory (more: global atomics)
+
+// buffer 0 of the column-extrema arrays of every fold that scans: +inf / -inf
+__global__ void k_fold_reset_cols(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restrict__ F, int nF) {
+  for (int q = blockIdx.x; q < nF; q += gridDim.x) {
+    const DfqFold f = F[q];
+    if (f.scan_go <= 0) continue;
+    const DfqLayer l = L[f.layer];
+    const int nch = (l.rows / f.scan_go) * f.scan_gi;
+    for (int j = threadIdx.x; j < nch; j += blockDim.x) { arena[l.cmin_off + j] = DFQ_INF; arena[l.cmax_off + j] = -DFQ_INF; }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, kPipeCtas)
 k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restrict__ F, int nF,
           const long long* __restrict__ tptr) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ float s_cmin[kFoldScanCols], s_cmax[kFoldScanCols];
   RowPipe pipe;
   pipe.init(pipe_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,12 +97,33 @@ k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restric
   TileDesc nd;
   if (threadIdx.x == 0)
     for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd); pipe.issue(nd); ahead.next(); }
+  // column scan of the folded rows (DfqFold.scan_go > 0): partial extrema per CTA and layer, flushed when the layer changes
+  for (int j = threadIdx.x; j < kFoldScanCols; j += kThreads) { s_cmin[j] = DFQ_INF; s_cmax[j] = -DFQ_INF; }
+  int cur = -1, nch = 0;
+  bool scanning = false, use_smem = false;
+  float *dmin = nullptr, *dmax = nullptr;
+  auto flush = [&]() {
+    if (!scanning || !use_smem) return;
+    __syncthreads();
+    colscan_flush<kThreads>(threadIdx.x, nch, s_cmin, s_cmax, dmin, dmax);
+    __syncthreads();
+  };
   while (it.valid()) {
     const int sidx = pipe.acquire();
     const TileDesc d = pipe.desc[sidx];
     const DfqFold f = F[d.task];
     const DfqLayer l = L[f.layer];
     const int row_len = l.cols * l.kk;
+    if (d.task != cur) {
+      flush();
+      cur = d.task;
+      scanning = f.scan_go > 0;
+      if (scanning) {
+        nch = (l.rows / f.scan_go) * f.scan_gi;
+        use_smem = nch <= kFoldScanCols;
+        dmin = arena + l.cmin_off; dmax = arena + l.cmax_off;    // buffer 0
+      }
+    }
     if (d.kind == TK_DIRECT) {
       for (int r = 0; r < d.nrows; ++r)
         fold_row<kThreads, true>(arena, l, f, d.gptr + (size_t)r * row_len, d.row0 + r, threadIdx.x);
@@ -97,6 +133,16 @@ k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restric
       for (int r = warp; r < d.nrows; r += kWarps)
         fold_row<32, false>(arena, l, f, pipe.stage[sidx] + (size_t)r * row_len, d.row0 + r, lane);
     }
+    if (scanning) {
+      __syncthreads();     // the tile's rows are final
+      const bool single = (f.scan_go == l.rows), own = (pipe_rows_per_tile(row_len) == 1);
+      if (d.kind == TK_DIRECT)
+        colscan_tile<kThreads, true>(d.gptr, threadIdx.x, d.row0, d.nrows, l.cols, l.kk, f.scan_go, f.scan_gi, single, own,
+                                     use_smem, s_cmin, s_cmax, dmin, dmax);
+      else
+        colscan_tile<kThreads, false>(pipe.stage[sidx], threadIdx.x, d.row0, d.nrows, l.cols, l.kk, f.scan_go, f.scan_gi, single,
+                                      own, use_smem, s_cmin, s_cmax, dmin, dmax);
+    }
     bool more = false;
     if (threadIdx.x == 0) {
       more = ahead.valid();
@@ -105,6 +151,7 @@ k_bn_fold(float* arena, const DfqLayer* __restrict__ L, const DfqFold* __restric
     pipe.release<true>(sidx, more, nd);
     it.next();
   }
+  flush();
   pipe.drain();
 }
 
@@ -267,7 +314,7 @@ __device__ __forceinline__ double bc_row(const float* __restrict__ row, int cols
 __global__ void __launch_bounds__(kThreads, kPipeCtas)
 k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __restrict__ B, int nB,
             const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits,
-            const long long* __restrict__ row_ptr) {
+            const long long* __restrict__ row_ptr, const long long* __restrict__ mm_ptr) {
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[2 * kWarps];
   __shared__ double dred[kWarps];
@@ -284,9 +331,19 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
     __stcg(arena + B[i].minmax_off + 1, -DFQ_INF);
   }
   grid.sync();
+  // layers whose column extrema the caller vouches for (DfqBcLayer.n_col > 0): reduce those, do not stream the weights
+  for (int bi = blockIdx.x; bi < nB; bi += gridDim.x) {
+    const DfqBcLayer b = B[bi];
+    if (b.n_col <= 0) continue;
+    float mn = DFQ_INF, mx = -DFQ_INF;
+    for (int j = threadIdx.x; j < b.n_col; j += kThreads) {
+      mn = fminf(mn, __ldcg(arena + b.colmin_off + j)); mx = fmaxf(mx, __ldcg(arena + b.colmax_off + j));
+    }
+    cta_minmax_atomic(mn, mx, arena + b.minmax_off, red);
+  }
   {
     MatIter<BcGeo> it;
-    it.start(row_ptr, 0, nB, BcGeo{arena, L, B});
+    it.start(mm_ptr, 0, nB, BcGeo{arena, L, B});   // mm_ptr: tile prefix with zero tiles for those layers
     MatIter<BcGeo> ahead = it;
     if (threadIdx.x == 0)
       for (int i = 0; i < kPipeStages - 1 && ahead.valid(); ++i) { ahead.fill(nd); pipe.issue(nd); ahead.next(); }
@@ -443,11 +500,20 @@ extern "C" int dfq_bn_fold(float* arena, int64_t arena_floats, const DfqLayer* l
   DFQ_REQUIRE(arena && layers && folds, "null argument");
   if (n_folds <= 0) return 0;
   std::vector<long long> tptr(n_folds + 1, 0);
+  bool any_scan = false;
   for (int i = 0; i < n_folds; ++i) {
     DFQ_REQUIRE(folds[i].layer >= 0 && folds[i].layer < n_layers, "fold layer index");
     const DfqLayer& l = layers[folds[i].layer];
     DFQ_REQUIRE(l.w_off >= 0 && l.w_off + (int64_t)l.rows * l.cols * l.kk <= arena_floats, "weight outside arena");
     tptr[i + 1] = tptr[i] + pipe_tiles(l.rows, l.cols * l.kk);
+    if (folds[i].scan_go > 0) {
+      const DfqFold& f = folds[i];
+      DFQ_REQUIRE(f.scan_gi > 0 && l.rows % f.scan_go == 0 && f.scan_gi == l.cols, "fold scan geometry (DfqRelation.go / .gi of the layer's rel_in)");
+      const int64_t nch = (int64_t)(l.rows / f.scan_go) * f.scan_gi;
+      DFQ_REQUIRE(l.cmin_off >= 0 && l.cmax_off >= 0 && l.cmin_off + 2 * nch <= arena_floats && l.cmax_off + 2 * nch <= arena_floats,
+                  "fold scan needs the layer's column range scratch");
+      any_scan = true;
+    }
   }
   int grid, rc;
   const size_t dyn = RowPipe::smem_bytes();
@@ -456,6 +522,7 @@ extern "C" int dfq_bn_fold(float* arena, int64_t arena_floats, const DfqLayer* l
   TablePack tp;
   const int iL = tp.add(layers, n_layers), iF = tp.add(folds, n_folds), iP = tp.add(tptr.data(), n_folds + 1);
   if ((rc = tp.upload(st))) return rc;
+  if (any_scan) k_fold_reset_cols<<<std::min(n_folds, 4096), 128, 0, st>>>(arena, tp.ptr<DfqLayer>(iL), tp.ptr<DfqFold>(iF), n_folds);
   k_bn_fold<<<grid, kThreads, dyn, st>>>(arena, tp.ptr<DfqLayer>(iL), tp.ptr<DfqFold>(iF), n_folds, tp.ptr<long long>(iP));
   DFQ_CUDA(cudaGetLastError());
   tp.release(st);
@@ -499,7 +566,7 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   if (n_bc <= 0 || n_levels <= 0) return 0;
   DFQ_REQUIRE(level_ptr[0] == 0 && level_ptr[n_levels] == n_bc, "levels must partition the layer list");
   int64_t max_tiles = 1;
-  std::vector<long long> row_ptr(n_bc + 1, 0);
+  std::vector<long long> row_ptr(n_bc + 1, 0), mm_ptr(n_bc + 1, 0);
   for (int i = 0; i < n_bc; ++i) {
     const DfqBcLayer& b = bc[i];
     DFQ_REQUIRE(b.layer >= 0 && b.layer < n_layers, "bc layer index");
@@ -511,6 +578,10 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
       DFQ_REQUIRE(terms[t].dst_off >= 0 && terms[t].dst_off + terms[t].n <= b.expect_len, "term outside expectation vector");
     DFQ_REQUIRE(b.expect_off >= 0 && b.expect_off + b.expect_len <= arena_floats, "expect scratch outside arena");
     row_ptr[i + 1] = row_ptr[i] + pipe_tiles(l.rows, l.cols * l.kk);
+    if (b.n_col > 0)
+      DFQ_REQUIRE(b.colmin_off >= 0 && b.colmax_off >= 0 && b.colmin_off + b.n_col <= arena_floats && b.colmax_off + b.n_col <= arena_floats,
+                  "column-extrema hint outside arena");
+    mm_ptr[i + 1] = mm_ptr[i] + (b.n_col > 0 ? 0 : pipe_tiles(l.rows, l.cols * l.kk));
   }
   max_tiles = std::max<int64_t>(max_tiles, row_ptr[n_bc]);
   int grid, rc;
@@ -519,11 +590,11 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   if ((rc = pick_grid((const void*)k_bc_engine, max_tiles, &grid, dyn))) return rc;
   TablePack tp;
   const int iL = tp.add(layers, n_layers), iB = tp.add(bc, n_bc), iT = tp.add(terms, n_terms);
-  const int iLP = tp.add(level_ptr, n_levels + 1), iRP = tp.add(row_ptr.data(), n_bc + 1);
+  const int iLP = tp.add(level_ptr, n_levels + 1), iRP = tp.add(row_ptr.data(), n_bc + 1), iMP = tp.add(mm_ptr.data(), n_bc + 1);
   if ((rc = tp.upload(st))) return rc;
   DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqBcLayer* dB = tp.ptr<DfqBcLayer>(iB); DfqExpectTerm* dT = tp.ptr<DfqExpectTerm>(iT);
-  int32_t* dLP = tp.ptr<int32_t>(iLP); long long* dRP = tp.ptr<long long>(iRP);
-  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP};
+  int32_t* dLP = tp.ptr<int32_t>(iLP); long long* dRP = tp.ptr<long long>(iRP); long long* dMP = tp.ptr<long long>(iMP);
+  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP, &dMP};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, dyn, st));
   tp.release(st);
   return 0;

@@ -39,6 +39,7 @@ class CleResult:
     last_diff: float
     diffs: List[float]       # diff_tmp per sweep of group 0
     group_sweeps: Optional[np.ndarray] = None
+    apply_only: bool = False
 
 
 @dataclass
@@ -201,12 +202,21 @@ class Session:
         return C.c_void_p(self.arena.data_ptr())
 
     # ---- BN fold --------------------------------------------------------------------------------------
-    def plan_bn_fold(self, folds: Sequence[dict]) -> dict:
+    def plan_bn_fold(self, folds: Sequence[dict], cle_plan: Optional[dict] = None) -> dict:
+        """cle_plan: the equalization plan that will run right after this fold.  The fold then also writes the column
+        extrema of every folded `second` layer (it has each tile in shared memory anyway) and `plan["scanned"]` lists those
+        layers: pass it to run_cle_plan(cols_ready=...) so that the equalization skips its initial 4 B/weight scan."""
         ft = np.zeros(len(folds), dtype=_lib.FOLD_DT)
+        scanned = []
         for i, f in enumerate(folds):
             for k in ft.dtype.names:
-                ft[i][k] = f[k]
-        return dict(ft=ft, lt=self._layer_table())
+                ft[i][k] = f.get(k, 0)
+            if cle_plan is not None:
+                ri = int(cle_plan["lt"][f["layer"]]["rel_in"])
+                if ri >= 0:
+                    ft[i]["scan_go"] = cle_plan["rt"][ri]["go"]; ft[i]["scan_gi"] = cle_plan["rt"][ri]["gi"]
+                    scanned.append(int(f["layer"]))
+        return dict(ft=ft, lt=cle_plan["lt"] if cle_plan is not None else self._layer_table(), scanned=scanned)
 
     def run_bn_fold(self, folds):
         """folds: dicts(layer, bn_eps, gamma_off, beta_off, mean_off, var_off, fake_w_off, fake_b_off), or a plan."""
@@ -286,8 +296,9 @@ class Session:
                     s_offs=s_offs, relations=list(relations), n_groups=n_groups)
 
     def run_cle_plan(self, plan: dict, s_range=(1e-8, 1e8), converge_thres=2e-7, converge_count=20, signed=False,
-                     eps=0, max_sweeps=0, apply_only=False) -> CleResult:
-        """Run dfq.py:78-117 on a planned relation list; see include/dfq_b200.h dfq_cle_run."""
+                     eps=0, max_sweeps=0, apply_only=False, cols_ready: Optional[Sequence[int]] = None) -> CleResult:
+        """Run dfq.py:78-117 on a planned relation list; see include/dfq_b200.h dfq_cle_run.
+        cols_ready: layers whose column extrema (buffer 0) a fold planned with cle_plan=plan has JUST written."""
         self._ensure_room()
         lo, hi = float(s_range[0]), float(s_range[1])
         P = np.zeros(1, dtype=_lib.CLE_PARAMS_DT)
@@ -301,6 +312,13 @@ class Session:
         P[0]["apply_only"] = 1 if apply_only else 0
         R = np.zeros(1, dtype=_lib.CLE_RESULT_DT)
         lt, rt = plan["lt"], plan["rt"]
+        if cols_ready:
+            key = tuple(cols_ready)
+            if plan.get("_ready_key") != key:
+                lt2 = lt.copy()
+                lt2["flags"][list(cols_ready)] |= _lib.LAYER_COLS_READY
+                plan["_ready_key"], plan["_ready_lt"] = key, lt2
+            lt = plan["_ready_lt"]
         gs = np.zeros(plan["n_groups"], dtype=np.int32)
         _lib.check(self.lib.dfq_cle_run(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
                                         _lib.table_ptr(rt), len(rt), _lib.table_ptr(plan["step_ptr"]),
@@ -310,7 +328,22 @@ class Session:
         n = int(R[0]["n_sweeps"])
         res = CleResult(n, bool(R[0]["converged"]), float(R[0]["last_diff"]), [float(x) for x in R[0]["diffs"][:min(n, 64)]])
         res.group_sweeps = gs
+        res.apply_only = bool(apply_only)
         return res
+
+    def cle_col_hints(self, plan: dict, res: CleResult) -> Optional[Dict[str, np.ndarray]]:
+        """The column extrema dfq_cle_run left for every `second` layer of `plan` (the buffer of parity
+        sweeps-of-its-group & 1), as parallel arrays dict(layer, colmin_off, colmax_off, n_col).  Valid until the weights
+        change again; hand it to run_bias_correct_plan(col_hints=...) so that the per-tensor range of dfq.py:14 is reduced
+        from C values instead of streaming the weights a second time."""
+        if res is None or res.n_sweeps <= 0 or res.apply_only or res.group_sweeps is None:
+            return None
+        lt, rt = plan["lt"], plan["rt"]
+        second = rt["second"].astype(np.int64)
+        Cn = rt["channels"].astype(np.int64)
+        par = (np.asarray(res.group_sweeps, dtype=np.int64)[lt["group"][second]] & 1)
+        return dict(layer=second, colmin_off=lt["cmin_off"][second] + par * Cn, colmax_off=lt["cmax_off"][second] + par * Cn,
+                    n_col=Cn)
 
     def run_cle(self, relations: Sequence[Tuple[int, int, int, int]], s_range=(1e-8, 1e8), converge_thres=2e-7,
                 converge_count=20, signed=False, eps=0, max_sweeps=0) -> Tuple[CleResult, List[int]]:
@@ -368,9 +401,19 @@ class Session:
         return dict(bt=bt, tt=tt, n_terms=len(terms), level_ptr=level_ptr, n_levels=len(uniq), delta_offs=delta_offs,
                     lt=self._layer_table())
 
-    def run_bias_correct_plan(self, plan: dict, num_bits: int = 8):
+    def run_bias_correct_plan(self, plan: dict, num_bits: int = 8, col_hints: Optional[Dict[str, np.ndarray]] = None):
+        """col_hints: see cle_col_hints (only meaningful for the layers' CURRENT weights)."""
         self._ensure_room()
         lt, bt, tt = plan["lt"], plan["bt"], plan["tt"]
+        if col_hints is not None and len(col_hints["layer"]):
+            bt = bt.copy()
+            lut = np.full(len(lt), -1, dtype=np.int64)
+            lut[col_hints["layer"]] = np.arange(len(col_hints["layer"]))
+            k = lut[bt["layer"]]
+            m = (k >= 0) & ((bt["flags"] & 1) == 0)          # bias absorption (raw sums) needs no range at all
+            for name in ("colmin_off", "colmax_off", "n_col"):
+                col = bt[name]
+                col[m] = col_hints[name][k[m]]
         _lib.check(self.lib.dfq_bias_correct(self._ptr(), self.arena.numel(), _lib.table_ptr(lt), len(lt),
                                              _lib.table_ptr(bt), len(bt), _lib.table_ptr(tt), plan["n_terms"],
                                              _lib.table_ptr(plan["level_ptr"]), plan["n_levels"], int(num_bits),

@@ -191,11 +191,12 @@ class DeviceStack:
         self.seed = seed
         folds = [dict(layer=li, bn_eps=1e-5, gamma_off=v["gamma"], beta_off=v["beta"], mean_off=v["mean"], var_off=v["var"],
                       fake_w_off=v["fake_w"], fake_b_off=v["fake_b"]) for li, v in zip(self.layers, self.vec)]
-        self.fold_plan = sess.plan_bn_fold(folds)
         rels = [(self.layers[2 * b], self.layers[2 * b + 1], self.vec[2 * b]["fake_w"], self.vec[2 * b]["fake_b"])
                 for b in range(n_blocks)]
         # every block is an independent model: its own convergence group (the reference would be called per model)
         self.cle_plan = sess.plan_cle(rels, groups=list(range(n_blocks)))
+        # the fold also writes the column extrema of every block's second conv: the equalization starts without a scan
+        self.fold_plan = sess.plan_bn_fold(folds, cle_plan=self.cle_plan)
         items = [dict(layer=self.layers[2 * b + 1], signed=False, level=0, next_bn_b_off=self.vec[2 * b + 1]["fake_b"],
                       terms=[dict(bn_w_off=self.vec[2 * b]["fake_w"], bn_b_off=self.vec[2 * b]["fake_b"], n=C, relu=True, op="set")])
                  for b in range(n_blocks)]
@@ -236,8 +237,9 @@ class DeviceStack:
         """One calibration step over the whole stack; returns the CleResult."""
         s = self.sess
         s.run_bn_fold(self.fold_plan)
-        res = s.run_cle_plan(self.cle_plan, converge_thres=converge_thres)
-        s.run_bias_correct_plan(self.bc_plan, 8)
+        res = s.run_cle_plan(self.cle_plan, converge_thres=converge_thres, cols_ready=self.fold_plan["scanned"])
+        # the corrected layers are the `second` convs: their range comes from the column extrema the equalization kept
+        s.run_bias_correct_plan(self.bc_plan, 8, col_hints=s.cle_col_hints(self.cle_plan, res))
         if self.quant_plan is not None:
             s.run_quantize(self.quant_plan)
         return res

@@ -72,7 +72,9 @@ typedef struct DfqLayer {
                          1 = depthwise middle (cols==1, one row per group) -> analytic as well
                          2 = general middle layer -> re-scanned after its pass               */
   int32_t group;      /* convergence group (= model) this layer belongs to, 0 .. n_groups-1    */
-  int32_t _pad;
+  int32_t flags;      /* DFQ_LAYER_COLS_READY: buffer 0 of cmin/cmax already holds the column extrema of the
+                         current weights (dfq_bn_fold with DfqFold.scan_go > 0 just produced them): dfq_cle_run
+                         skips its initial scan of this layer                                  */
   int64_t cmin_off;   /* [2][C of rel_in] running column minima, double-buffered by sweep parity
                          (scratch, valid when rel_in >= 0)                                  */
   int64_t cmax_off;   /* [2][C of rel_in] running column maxima                              */
@@ -80,6 +82,8 @@ typedef struct DfqLayer {
 
 /* One equalization relation (utils/relation.py:5-27): rows of `first` are multiplied by s[c],
  * the matching input columns of `second` by 1/s[c] (dfq.py:62-73). */
+#define DFQ_LAYER_COLS_READY 1
+
 typedef struct DfqRelation {
   int32_t first;
   int32_t second;
@@ -147,6 +151,10 @@ typedef struct DfqFold {
   float bn_eps;
   int64_t gamma_off, beta_off, mean_off, var_off;   /* inputs  [rows] */
   int64_t fake_w_off, fake_b_off;                   /* outputs [rows] */
+  int32_t scan_go, scan_gi;   /* > 0: the layer is `second` of a relation with `scan_go` rows and `scan_gi` columns per
+                                 group (DfqRelation.go / .gi): also write the column extrema of the FOLDED weights into
+                                 buffer 0 of the layer's cmin_off / cmax_off (layers[] must carry them), saving the
+                                 equalization its initial 4 B/weight scan.  0: no scan. */
 } DfqFold;
 int dfq_bn_fold(float* arena, int64_t arena_floats, const DfqLayer* layers, int32_t n_layers,
                 const DfqFold* folds, int32_t n_folds, void* stream);
@@ -179,6 +187,10 @@ typedef struct DfqBcLayer {
   int64_t delta_off;         /* scratch/out [rows]: eps . E[x]                           */
   int64_t next_bn_b_off;     /* fake_bias that receives -delta (dfq.py:204-206), or -1  */
   int64_t minmax_off;        /* scratch [2]: per-tensor min/max of W                     */
+  int64_t colmin_off;        /* n_col > 0: [n_col] column minima / maxima of the CURRENT weights that the caller vouches */
+  int64_t colmax_off;        /* for; the per-tensor range (dfq.py:14) is reduced from them and the weights are not      */
+  int32_t n_col;             /* streamed a second time.  After dfq_cle_run the valid buffer of a `second` layer is      */
+  int32_t _pad;              /* cmin_off + (group_sweeps[group] & 1) * C (same for cmax).  0: scan the weights.          */
 } DfqBcLayer;
 int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLayer* layers, int32_t n_layers,
                      const DfqBcLayer* bc, int32_t n_bc, const DfqExpectTerm* terms, int32_t n_terms,

@@ -37,6 +37,7 @@ def _val(x):
 class FakeLib:
     def __init__(self, sqrt_fn=None):
         self.calls = []
+        self.stats = {}     # protocol counters: "cols_ready" (layers that arrived pre-scanned), "hinted" (ranges taken from hints)
         # None = IEEE sqrt (what the GPU computes); tests comparing with reference fixtures inject the HOST's
         # torch.sqrt (MKL VML, faithful but not correctly rounded) to reproduce the reference bit for bit
         self.sqrt_fn = sqrt_fn
@@ -53,6 +54,14 @@ class FakeLib:
         n = int(l["rows"]) * int(l["cols"]) * int(l["kk"])
         return arena[int(l["w_off"]): int(l["w_off"]) + n].reshape(int(l["rows"]), int(l["cols"]), int(l["kk"]))
 
+    @staticmethod
+    def _col_extrema(w, go, gi):
+        """[C] column minima / maxima of a `second` layer (rows in groups of `go`, gi columns per group)."""
+        rows = w.shape[0]
+        G = rows // go
+        v = w.reshape(G, go, gi, -1)
+        return v.min(axis=(1, 3)).reshape(-1).astype(f32), v.max(axis=(1, 3)).reshape(-1).astype(f32)
+
     def dfq_cle_run(self, arena_p, n_arena, lt_p, nL, rt_p, nR, sp_p, sl_p, n_steps, P_p, R_p, n_groups, gs_p, stream):
         self.calls.append("dfq_cle_run")
         arena = _floats(arena_p, n_arena)
@@ -62,6 +71,15 @@ class FakeLib:
         sl = np.ctypeslib.as_array((C.c_int32 * int(sp[n_steps])).from_address(int(_val(sl_p))))
         P = _table(P_p, 1, _lib.CLE_PARAMS_DT)[0]
         res = _table(R_p, 1, _lib.CLE_RESULT_DT)
+        # protocol check: a layer flagged COLS_READY must arrive with buffer 0 = the column extrema of its current weights
+        for r in R:
+            l2 = L[int(r["second"])]
+            if int(l2["flags"]) & _lib.LAYER_COLS_READY:
+                Cn = int(r["channels"])
+                cmn, cmx = self._col_extrema(self._wview(arena, l2), int(r["go"]), int(r["gi"]))
+                assert np.array_equal(arena[int(l2["cmin_off"]): int(l2["cmin_off"]) + Cn], cmn), "COLS_READY but stale column minima"
+                assert np.array_equal(arena[int(l2["cmax_off"]): int(l2["cmax_off"]) + Cn], cmx), "COLS_READY but stale column maxima"
+                self.stats["cols_ready"] = self.stats.get("cols_ready", 0) + 1
         used = sorted(set(int(x) for x in sl))
         remap = {li: k for k, li in enumerate(used)}
         layers = []
@@ -115,6 +133,14 @@ class FakeLib:
             n = max(n, ng)
         for r, rel in zip(R, rels):
             arena[int(r["s_acc_off"]): int(r["s_acc_off"]) + int(r["channels"])] = rel.S
+            # like the device: the column extrema of the final weights sit in buffer (sweeps of the group & 1); poison the other
+            l2 = L[int(r["second"])]
+            Cn = int(r["channels"])
+            ng = int(gs[int(l2["group"])]) if gs is not None else n
+            cmn, cmx = self._col_extrema(self._wview(arena, l2), int(r["go"]), int(r["gi"]))
+            for off, val in ((int(l2["cmin_off"]), cmn), (int(l2["cmax_off"]), cmx)):
+                arena[off + (ng & 1) * Cn: off + (ng & 1) * Cn + Cn] = val
+                arena[off + ((ng & 1) ^ 1) * Cn: off + ((ng & 1) ^ 1) * Cn + Cn] = np.nan
         res[0]["n_sweeps"] = n
         res[0]["converged"] = 0 if (int(P["max_sweeps"]) and n >= int(P["max_sweeps"]) and diffs and diffs[-1] > float(P["converge_thres"])) else 1
         res[0]["last_diff"] = diffs[-1] if diffs else 10.0
@@ -137,6 +163,10 @@ class FakeLib:
                                        v(f["var_off"]), float(f["bn_eps"]))
             w[...] = w2; b[...] = b2
             v(f["fake_w_off"])[...] = fw; v(f["fake_b_off"])[...] = fb
+            if int(f["scan_go"]) > 0:     # column extrema of the folded weights -> buffer 0
+                cmn, cmx = self._col_extrema(w, int(f["scan_go"]), int(f["scan_gi"]))
+                arena[int(l["cmin_off"]): int(l["cmin_off"]) + cmn.size] = cmn
+                arena[int(l["cmax_off"]): int(l["cmax_off"]) + cmx.size] = cmx
         return 0
 
     def dfq_bias_correct(self, arena_p, n_arena, lt_p, nL, bt_p, nB, tt_p, nT, lp_p, n_levels, num_bits, stream):
@@ -164,6 +194,11 @@ class FakeLib:
                 l = L[int(b["layer"])]
                 rows = int(l["rows"])
                 w = self._wview(arena, l)
+                if int(b["n_col"]) > 0:   # the caller vouches for these column extrema: they must give the tensor's range
+                    hmn = arena[int(b["colmin_off"]): int(b["colmin_off"]) + int(b["n_col"])]
+                    hmx = arena[int(b["colmax_off"]): int(b["colmax_off"]) + int(b["n_col"])]
+                    assert hmn.min() == w.min() and hmx.max() == w.max(), "column-extrema hint does not match the weights"
+                    self.stats["hinted"] = self.stats.get("hinted", 0) + 1
                 if int(b["flags"]) & 1:
                     d = O.bias_absorb_wc(w, expects[bi], expects[bi].shape[0])
                 else:

@@ -283,3 +283,78 @@ def test_large_stack_properties():
     res2 = sess.run_cle_plan(st.cle_plan)
     assert int(res2.group_sweeps.max()) == 1
     assert torch.allclose(sess.view(st.w_begin, 2 * N), before, rtol=1e-6, atol=0)
+
+
+FUSED_CHAINS = CHAINS + [
+    [(24, 16, 3, 3), (12, 24, 32, 32)],        # second layer with rows longer than a stage (9216 floats): direct path
+    [(33, 7, 3, 3), (21, 33, 3, 3)],           # unaligned tiles (297-float rows at odd offsets): cooperative path
+]
+
+
+@pytest.mark.parametrize("shapes", FUSED_CHAINS)
+def test_fused_fold_scan_and_range_hints_equal_the_unfused_calls(shapes):
+    """fold -> equalize -> correct with the two shortcuts of the fused plan (the fold pre-scans the column extrema the
+    equalization starts from; the correction takes per-tensor ranges from the column extrema the equalization leaves) must
+    give bit-identical results to the three plain calls, and the fold's column extrema must be the true ones."""
+    from dfq_b200.engine import Session
+
+    def build():
+        sess = Session()
+        ws, bs, _ = _chain_case(shapes, 23)
+        g = torch.Generator().manual_seed(5)
+        ids, vecs = [], []
+        for w, b in zip(ws, bs):
+            ids.append(sess.add_layer(w, b))
+            n = w.shape[0]
+            v = dict(gamma=sess.bind(torch.rand(n, generator=g) + 0.5, False), beta=sess.bind(torch.randn(n, generator=g) * 0.2, False),
+                     mean=sess.bind(torch.randn(n, generator=g) * 0.1, False), var=sess.bind(torch.rand(n, generator=g) + 0.5, False),
+                     fake_w=sess.alloc(n), fake_b=sess.alloc(n))
+            vecs.append(v)
+        folds = [dict(layer=li, bn_eps=1e-5, gamma_off=v["gamma"], beta_off=v["beta"], mean_off=v["mean"], var_off=v["var"],
+                      fake_w_off=v["fake_w"], fake_b_off=v["fake_b"]) for li, v in zip(ids, vecs)]
+        rels = [(ids[i], ids[i + 1], vecs[i]["fake_w"], vecs[i]["fake_b"]) for i in range(len(ids) - 1)]
+        items = [dict(layer=ids[i], signed=False, level=i, next_bn_b_off=vecs[i]["fake_b"],
+                      terms=[dict(bn_w_off=vecs[i - 1]["fake_w"], bn_b_off=vecs[i - 1]["fake_b"], n=ws[i - 1].shape[0], relu=True, op="set")])
+                 for i in range(1, len(ids))]
+        return sess, ws, bs, ids, vecs, folds, rels, items
+
+    # plain
+    sa, wa, ba, ida, va, folds, rels, items = build()
+    cle_a = sa.plan_cle(rels); bc_a = sa.plan_bias_correct(items); fold_a = sa.plan_bn_fold(folds)
+    sa.upload()
+    sa.run_bn_fold(fold_a)
+    res_a = sa.run_cle_plan(cle_a)
+    sa.run_bias_correct_plan(bc_a, 8)
+    fb_a = [sa.view(v["fake_b"], w.shape[0]).cpu().numpy() for v, w in zip(va, wa)]
+    sa.download()
+    # fused
+    sb, wb, bb, idb, vb, folds, rels, items = build()
+    cle_b = sb.plan_cle(rels); bc_b = sb.plan_bias_correct(items); fold_b = sb.plan_bn_fold(folds, cle_plan=cle_b)
+    assert sorted(fold_b["scanned"]) == sorted(idb[1:])
+    sb.upload()
+    sb.run_bn_fold(fold_b)
+    for i in range(1, len(idb)):               # buffer 0 of every `second` layer = true column extrema of the folded weights
+        l = cle_b["lt"][idb[i]]; r = cle_b["rt"][int(l["rel_in"])]
+        n = int(l["rows"]) * int(l["cols"]) * int(l["kk"])
+        w = sb.view(int(l["w_off"]), n).cpu().numpy().reshape(int(r["groups"]), int(r["go"]), int(r["gi"]), -1)
+        Cn = int(r["channels"])
+        assert np.array_equal(sb.view(int(l["cmin_off"]), Cn).cpu().numpy(), w.min(axis=(1, 3)).reshape(-1))
+        assert np.array_equal(sb.view(int(l["cmax_off"]), Cn).cpu().numpy(), w.max(axis=(1, 3)).reshape(-1))
+    res_b = sb.run_cle_plan(cle_b, cols_ready=fold_b["scanned"])
+    hints = sb.cle_col_hints(cle_b, res_b)
+    assert sorted(hints["layer"].tolist()) == sorted(idb[1:])
+    for li, mn_off, mx_off, Cn in zip(*(hints[k].tolist() for k in ("layer", "colmin_off", "colmax_off", "n_col"))):
+        # what the equalization left = true column extrema of the final weights
+        l = cle_b["lt"][li]; r = cle_b["rt"][int(l["rel_in"])]
+        n = int(l["rows"]) * int(l["cols"]) * int(l["kk"])
+        w = sb.view(int(l["w_off"]), n).cpu().numpy().reshape(int(r["groups"]), int(r["go"]), int(r["gi"]), -1)
+        assert np.array_equal(sb.view(mn_off, Cn).cpu().numpy(), w.min(axis=(1, 3)).reshape(-1))
+        assert np.array_equal(sb.view(mx_off, Cn).cpu().numpy(), w.max(axis=(1, 3)).reshape(-1))
+    sb.run_bias_correct_plan(bc_b, 8, col_hints=hints)
+    fb_b = [sb.view(v["fake_b"], w.shape[0]).cpu().numpy() for v, w in zip(vb, wb)]
+    sb.download()
+    assert res_a.n_sweeps == res_b.n_sweeps
+    for x, y in zip(wa + ba, wb + bb):
+        assert np.array_equal(x.numpy(), y.numpy())
+    for x, y in zip(fb_a, fb_b):
+        assert np.array_equal(x, y)

@@ -189,7 +189,7 @@ def test_quantize_function_and_observer_follow_reference_fixture(monkeypatch):
 def test_graph_calibration_equals_the_four_separate_calls(monkeypatch):
     """dfq_b200.calibrate.GraphCalibration (one staging, fused plan) == merge_batchnorm + create_relation +
     cross_layer_equalization + bias_correction + quantize_targ_layer called one after the other."""
-    fakelib.install(monkeypatch)
+    fake = fakelib.install(monkeypatch)
     from dfq_b200 import dfq
     from dfq_b200.calibrate import GraphCalibration
     from dfq_b200.utils import layer_transform as LT
@@ -204,7 +204,11 @@ def test_graph_calibration_equals_the_four_separate_calls(monkeypatch):
     dfq.bias_correction(ga, ba, targ)
     LT.quantize_targ_layer(ga, 8, 16, targ)
     cal = GraphCalibration(gb, bb, targ)
+    fake.stats.clear()
     res = cal.run(equalize=True, correction=True, quantize_bits=(8, 16))
+    # the fused plan's shortcuts were taken (and verified inside the fake): the fold pre-scanned every `second` layer, and the
+    # correction took those layers' ranges from the column extrema the equalization left behind
+    assert fake.stats.get("cols_ready", 0) == len(cal.relations) and fake.stats.get("hinted", 0) > 0
     assert res.n_sweeps == dfq.cross_layer_equalization.last_result.n_sweeps
     assert len(cal.relations) == len(rels)
     for ra, rb in zip(rels, cal.relations):
