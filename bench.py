@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--layers", type=int, default=4096, help="Conv/BN pairs in the synthetic stack per GPU")
     p.add_argument("--e2e-layers", type=int, default=512, help="pairs moved host->device->host per e2e step")
+    p.add_argument("--e2e-chunk", type=int, default=32, help="pairs per pipelined chunk of the e2e arm")
+    p.add_argument("--e2e-slots", type=int, default=4, help="arena slots of the e2e pipeline")
     p.add_argument("--cpu-layers", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--quantize", action="store_true", help="also fake-quantize weights/biases (8 bit) inside the step")
@@ -325,19 +327,19 @@ def run_b200(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         from dfq_b200.workload import HostStackCalibrator
-        chunk_blocks = 32                                         # 64 layer pairs = 604 MB per chunk
+        chunk_blocks = max(1, args.e2e_chunk // 2)                # 32 layer pairs = 302 MB per chunk
         n_chunks = max(2, min(args.e2e_layers, layers) // (2 * chunk_blocks))
         e_layers = n_chunks * 2 * chunk_blocks
         del pristine
         torch.cuda.empty_cache()
-        hc = HostStackCalibrator(dev, chunk_blocks, C, K, quantize=args.quantize)
+        hc = HostStackCalibrator(dev, chunk_blocks, C, K, quantize=args.quantize, n_slots=args.e2e_slots)
         n_state = hc.chunk_floats * n_chunks
         host_in = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
         host_out = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
         for st_ in hc.slots:
             st_.generate()
         for i in range(n_chunks):                                 # synthetic host image (chunks repeat two seeds)
-            host_in[i * hc.chunk_floats:(i + 1) * hc.chunk_floats].copy_(hc.slots[i % 2].state())
+            host_in[i * hc.chunk_floats:(i + 1) * hc.chunk_floats].copy_(hc.slots[i % len(hc.slots)].state())
         torch.cuda.synchronize()
 
         def e2e_step():
@@ -358,8 +360,8 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": world * e_layers / (float(tt[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * n_state,
                "d2h_bytes_per_step": 4 * n_state, "layers_per_step": e_layers, "ms_per_step": float(tt[0]),
                "pcie_GBps_each_way": 4e-9 * n_state / (float(tt[0]) * 1e-3),
-               "api": "dfq_b200.workload.HostStackCalibrator.run(pinned_in, pinned_out): 64-pair chunks, H2D / kernels / "
-                      "D2H pipelined on three streams"}
+               "api": "dfq_b200.workload.HostStackCalibrator.run(pinned_in, pinned_out): %d-pair chunks, H2D / kernels / "
+                      "D2H pipelined on three streams over %d arena slots" % (2 * chunk_blocks, args.e2e_slots)}
         del hc, host_in, host_out
 
     launches_per_step = stack.launches_per_step

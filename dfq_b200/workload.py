@@ -253,15 +253,19 @@ class HostStackCalibrator:
     """Calibrate a stack that lives in HOST memory, streaming it through the GPU in chunks.
 
     The host image is the concatenation of per-chunk state images (what ``DeviceStack.state()`` looks like).  Three
-    streams form a pipeline over the chunks: H2D of chunk i+1 (pinned -> arena B), the kernels on chunk i (arena A),
-    D2H of chunk i-1.  PCIe is full duplex, so a step is bound by max(H2D, D2H, compute) per chunk instead of their sum.
+    streams form a pipeline over the chunks: H2D of chunk i+1, the kernels on chunk i, D2H of chunk i-1, each chunk in its
+    own arena slot.  THREE slots are needed for the two copy directions to overlap (with two, the load of chunk i+1 has to
+    wait for the store of chunk i-1 to vacate its slot); PCIe is full duplex, so a step is then bound by
+    max(H2D, D2H, compute) per chunk instead of their sum.
     """
 
-    def __init__(self, device, chunk_blocks: int = 32, channels: int = 512, k: int = 3, quantize: bool = False):
+    def __init__(self, device, chunk_blocks: int = 32, channels: int = 512, k: int = 3, quantize: bool = False,
+                 n_slots: int = 4):
         from .engine import Session
         self.device = device
         self.slots = []
-        for _ in range(2):
+        self.n_slots = n_slots
+        for _ in range(n_slots):
             sess = Session(device)
             st = DeviceStack(sess, chunk_blocks, channels, k, quantize=quantize)
             self.slots.append(st)
@@ -274,7 +278,7 @@ class HostStackCalibrator:
     def run(self, host_in: torch.Tensor, host_out: torch.Tensor):
         """host_in/host_out: pinned fp32 tensors of n_chunks * chunk_floats elements."""
         n = host_in.numel() // self.chunk_floats
-        F = self.chunk_floats
+        F, S = self.chunk_floats, self.n_slots
         loaded = [torch.cuda.Event() for _ in range(n)]
         computed = [torch.cuda.Event() for _ in range(n)]
         stored = [torch.cuda.Event() for _ in range(n)]
@@ -283,9 +287,9 @@ class HostStackCalibrator:
 
         def load(i):
             with torch.cuda.stream(self.s_in):
-                if i >= 2:
-                    self.s_in.wait_event(stored[i - 2])          # the slot's previous tenant has left
-                self.slots[i % 2].state().copy_(host_in[i * F:(i + 1) * F], non_blocking=True)
+                if i >= S:
+                    self.s_in.wait_event(stored[i - S])          # the slot's previous tenant has left
+                self.slots[i % S].state().copy_(host_in[i * F:(i + 1) * F], non_blocking=True)
                 loaded[i].record(self.s_in)
 
         load(0)
@@ -294,10 +298,10 @@ class HostStackCalibrator:
                 load(i + 1)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(loaded[i])
-                self.slots[i % 2].run()                           # returns when the equalization result is back
+                self.slots[i % S].run()                           # returns when the equalization result is back
                 computed[i].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(computed[i])
-                host_out[i * F:(i + 1) * F].copy_(self.slots[i % 2].state(), non_blocking=True)
+                host_out[i * F:(i + 1) * F].copy_(self.slots[i % S].state(), non_blocking=True)
                 stored[i].record(self.s_out)
         cur.wait_stream(self.s_out)
