@@ -262,6 +262,11 @@ constexpr int kRowRegs = (kStageFloats / 4 + kThreads - 1) / kThreads;
 #define DFQ_TMA_STORE 1
 #endif
 constexpr bool kTmaStore = DFQ_TMA_STORE != 0;
+// General middle layers (row- AND column-scaled, cols > 1) need their column extrema recomputed every sweep.  With the bulk
+// store the rescaled tile sits in its stage anyway: the extrema are accumulated right there (no second read of the layer, no
+// extra grid-wide phase).  Without it (DFQ_TMA_STORE=0) a separate scan phase follows the layer's pass.
+constexpr bool kFuseRescan = kTmaStore;
+constexpr int kRescanCols = 1024;   // columns a team accumulates in shared memory (more: global atomics)
 constexpr size_t kTableCacheBytes = 9 * 1024;   // descriptor tables of a model this small are mirrored in shared memory
 constexpr int TK_END = 3;   // sentinel tile: the pass is over for this CTA (the consumers keep no iterator of their own)
 static_assert(kThreads * kRowRegs * 4 >= kStageFloats, "a single-row tile must fit the consumers' registers");
@@ -380,8 +385,13 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
 //               to the producer warp (mailbox again)
 //   many rows : a warp per row, 32 rows per batch -- lane j fetches row j's inputs before the batch and does row j's
 //               bookkeeping after it, so a batch pays TWO global-memory latencies instead of two per row
+#ifdef DFQ_NOINLINE_TILE
+#define DFQ_TILE_INLINE __noinline__
+#else
+#define DFQ_TILE_INLINE __forceinline__
+#endif
 template <int MODE, bool HAS_OUT>
-__device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams P, float* buf, float* g, int row0,
+__device__ DFQ_TILE_INLINE void cle_tile_rows(const RowCtx& c, const DfqCleParams& P, float* buf, float* g, int row0,
                                               int nrows, const float* s_inv, float* red, int& parity, double& dacc,
                                               StagePub* pub, uint64_t* done) {
   const int warp = ctid() >> 5, lane = ctid() & 31;
@@ -573,6 +583,7 @@ struct PassIter {
   long long q_lo, q_hi;   // tile range of task q, cached: the per-tile advance touches no global memory
   TileCursor cur;
   int q_live;   // last task whose group was checked and found still iterating (one uncached read per layer, not per tile)
+  int g_seen, g_done;   // ... and per run of layers of the same group, not per layer
   __device__ __forceinline__ void settle() {
     while (cur.valid()) {
       if (cur.t >= q_hi) {
@@ -580,14 +591,16 @@ struct PassIter {
         q_lo = ptr[q]; q_hi = ptr[q + 1];
       }
       if (q != q_live) {
-        if (*((volatile const int*)&G[L[step_layers[q]].group].done)) { cur.seek(q_hi); continue; }
+        const int g = L[step_layers[q]].group;
+        if (g != g_seen) { g_done = *((volatile const int*)&G[g].done); g_seen = g; }   // flags only change between sweeps
+        if (g_done) { cur.seek(q_hi); continue; }
         q_live = q;
       }
       break;
     }
   }
   __device__ __forceinline__ void start(const long long* p, const int* sl, const DfqLayer* L_, const GroupState* G_, int qb, int qe) {
-    ptr = p; step_layers = sl; L = L_; G = G_; q_end = qe; q_live = -1;
+    ptr = p; step_layers = sl; L = L_; G = G_; q_end = qe; q_live = -1; g_seen = -1; g_done = 0;
     cur.init(p[qb], p[qe]);
     q = cur.valid() ? find_task(p, qb, qe, cur.t) : qb;
     q_lo = p[q]; q_hi = (q < qe) ? p[q + 1] : p[q];
@@ -728,23 +741,30 @@ __device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, cons
 }
 
 __global__ void __launch_bounds__(kCtaThreads, kCleCtas)
-k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int nR,
-             const int* step_ptr, const int* step_layers, int n_steps,
-             const int* step_rescan, const long long* pass_ptr,
-             const long long* scan_ptr, const int* scan_layers, int n_scan,
-             DfqCleParams P, CleCtl* ctl, GroupState* G, int nG, const unsigned char* tbl, int tbl_bytes) {
+k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRelation* __restrict__ gR, int nR,
+             const int* __restrict__ g_step_ptr, const int* __restrict__ g_step_layers, int n_steps,
+             const int* __restrict__ g_step_rescan, const long long* __restrict__ g_pass_ptr,
+             const long long* __restrict__ g_scan_ptr, const int* __restrict__ g_scan_layers, int n_scan,
+             DfqCleParams P, CleCtl* ctl, GroupState* G, int nG, int rs_cols, const unsigned char* tbl, int tbl_bytes) {
   cg::grid_group grid = cg::this_grid();
   // per-team scratch
   __shared__ float red_all[kTeams][2 * 2 * 8];
   __shared__ double dred_all[kTeams][8];
   __shared__ RowCtx sctx_all[kTeams];
   __shared__ __align__(16) float s_inv_all[kTeams][kInvCache + 4];   // 1/s of the current layer's input columns
+  struct RescanCtx { float *dmin, *dmax; int nch, go, gi; bool smem, own, single; };
+  __shared__ RescanCtx rsx_all[kTeams];
   const int tm = threadIdx.x < kTeams * kThreads ? team() : 0;
+  RescanCtx& rsx = rsx_all[tm];
   float* red = red_all[tm];
   double* dred = dred_all[tm];
   RowCtx& sctx = sctx_all[tm];
   float* s_inv = s_inv_all[tm];
   extern __shared__ __align__(128) unsigned char pipe_smem[];
+  // scratch of the fused re-scan: rs_cols columns per team behind the ring, only when the problem has re-scanned layers
+  // (the host sizes the dynamic shared memory; without them the CTA stays at 64 KB and the SM keeps a 60 KB L1)
+  float* rs_min = (float*)(pipe_smem + ((WsPipe::smem_bytes() + 15) & ~(size_t)15)) + (size_t)tm * 2 * rs_cols;
+  float* rs_max = rs_min + rs_cols;
   // the column-scan scratch aliases the reciprocal-scale cache: scans and passes never overlap
   float* smin = s_inv;
   float* smax = s_inv + kScanCols;
@@ -752,17 +772,24 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
   WsPipe ws;
   ws.init(pipe_smem);
   // A small model is latency-bound: every phase walks the descriptor tables with dependent loads.  When the whole table pack
-  // fits (the host decides, tbl_bytes > 0) it is copied into shared memory once and every table pointer is moved onto the copy.
+  // fits (the host decides: tbl_bytes > 0) it is mirrored in shared memory behind the ring.  The table pointers below are pure
+  // functions of kernel arguments (cheap to rematerialise, nothing held in registers across the tile loop), and derived from
+  // the shared-memory base, not from the arguments: kernel pointer arguments are assumed to point to global memory.
+  unsigned char* tcache = pipe_smem + ((WsPipe::smem_bytes() + 15) & ~(size_t)15) + (size_t)kTeams * 2 * rs_cols * sizeof(float);
   if (tbl_bytes > 0) {
-    unsigned char* cache = pipe_smem + ((WsPipe::smem_bytes() + 255) & ~(size_t)255);
-    for (int i = threadIdx.x * 16; i < tbl_bytes; i += kCtaThreads * 16) *(int4*)(cache + i) = *(const int4*)(tbl + i);
+    for (int i = threadIdx.x * 16; i < tbl_bytes; i += kCtaThreads * 16) *(int4*)(tcache + i) = *(const int4*)(tbl + i);
     __syncthreads();
-    // (derive the new pointers from `cache`, not from the kernel arguments: those are assumed to point to global memory)
-#define DFQ_MOVE(ptr) ptr = (decltype(ptr))(cache + ((const unsigned char*)(ptr) - tbl))
-    DFQ_MOVE(L); DFQ_MOVE(R); DFQ_MOVE(step_ptr); DFQ_MOVE(step_layers); DFQ_MOVE(step_rescan); DFQ_MOVE(pass_ptr);
-    DFQ_MOVE(scan_ptr); DFQ_MOVE(scan_layers);
-#undef DFQ_MOVE
   }
+#define DFQ_TAB(T, g) (tbl_bytes > 0 ? (const T*)(tcache + ((const unsigned char*)(g) - tbl)) : (const T*)(g))
+  const DfqLayer* L = DFQ_TAB(DfqLayer, gL);
+  const DfqRelation* R = DFQ_TAB(DfqRelation, gR);
+  const int* step_ptr = DFQ_TAB(int, g_step_ptr);
+  const int* step_layers = DFQ_TAB(int, g_step_layers);
+  const int* step_rescan = DFQ_TAB(int, g_step_rescan);
+  const long long* pass_ptr = DFQ_TAB(long long, g_pass_ptr);
+  const long long* scan_ptr = DFQ_TAB(long long, g_scan_ptr);
+  const int* scan_layers = DFQ_TAB(int, g_scan_layers);
+#undef DFQ_TAB
   const bool producer = threadIdx.x >= kTeams * kThreads;
   int parity = 0;
   const int warp = ctid() >> 5, lane = ctid() & 31;
@@ -776,6 +803,7 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
   // ---- phase 0: column extrema of every `second` layer (buffer 0) -----------------------------
   if (!producer) {
     for (int g = vblock() * kThreads + ctid(); g < nG; g += vgrid() * kThreads) G[g].diff = 10.0;   // dfq.py:81
+    for (int j = ctid(); j < rs_cols; j += kThreads) { rs_min[j] = DFQ_INF; rs_max[j] = -DFQ_INF; }
     for (int li = vblock(); li < nL; li += vgrid())
       if (L[li].rel_in >= 0 && !(L[li].flags & DFQ_LAYER_COLS_READY)) reset_cols(arena, L[li], R[L[li].rel_in], 0);
   }
@@ -867,6 +895,18 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
           dacc = 0.0;
         };
         int cur_li = -1, in_mode = IN_NONE;
+        // fused re-scan of the layer in hand (col_mode 2): partial column extrema of its NEW rows, flushed when the layer changes
+        // (its geometry lives in shared memory, written by the team leader at the layer change: the tile loop is short of registers)
+        int rs_li = -1;
+        auto rs_flush = [&]() {
+          if (rs_li < 0) return;
+          if (rsx.smem) {
+            cbar();
+            colscan_flush<kThreads>(ctid(), rsx.nch, rs_min, rs_max, rsx.dmin, rsx.dmax);
+            cbar();
+          }
+          rs_li = -1;
+        };
 #ifdef DFQ_TILE_TRACE
         const bool tr = (blockIdx.x == 0 && threadIdx.x == 0 && sweep == 0 && p == 0);
         int trn = 0;
@@ -879,7 +919,8 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
           DFQ_TT(0);
           mbar_wait(ws.full(sidx), (uint32_t)((count / kCleStages) & 1));
           DFQ_TT(1);
-          const TileDesc d = *ws.desc(sidx);
+          // the descriptor stays in shared memory (valid until `done` is arrived): the loop is short of registers
+          const volatile TileDesc& d = *ws.desc(sidx);
           if (d.kind == TK_END) { mbar_arrive(ws.done(sidx)); count += 1 + d.nrows; break; }
           float* buf = ws.stage(sidx);
           if (d.kind == TK_PLAIN) {            // a tile the TMA unit cannot move: cooperative fetch
@@ -904,12 +945,38 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
               if (ctid() == 0) s_inv[sctx.cols] = 1.f;
               cbar();
             }
-            if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0)
+            if (kFuseRescan) {
+              rs_flush();
+              const DfqLayer l = L[cur_li];
+              if (l.col_mode == 2 && l.rel_in >= 0) {       // accumulate into the NEXT sweep's buffer, reset one step ago
+                rs_li = cur_li;
+                if (ctid() == 0) {
+                  const DfqRelation r = R[l.rel_in];
+                  rsx.nch = r.channels; rsx.go = r.go; rsx.gi = r.gi;
+                  rsx.single = (r.groups == 1); rsx.smem = (r.channels <= rs_cols);
+                  rsx.own = (pipe_rows_per_tile(l.cols * l.kk) == 1);
+                  rsx.dmin = arena + l.cmin_off + (size_t)((sweep & 1) ^ 1) * r.channels;
+                  rsx.dmax = arena + l.cmax_off + (size_t)((sweep & 1) ^ 1) * r.channels;
+                }
+                cbar();
+              }
+            } else if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0) {
               reset_cols(arena, L[cur_li], R[L[cur_li].rel_in], (sweep & 1) ^ 1);
+            }
+          }
+          // the re-scanned successor's next-sweep buffer is reset HERE, one step (= one grid barrier) before its pass fills it
+          if (kFuseRescan && d.row0 == 0 && sctx.has_out) {
+            const DfqRelation ro = R[L[cur_li].rel_out];
+            if (L[ro.second].col_mode == 2) reset_cols(arena, L[ro.second], ro, (sweep & 1) ^ 1);
           }
           const RowCtx& c = sctx;
           if (d.kind == TK_DIRECT) {
             for (int r = 0; r < d.nrows; ++r) cle_row_generic(c, P, d.row0 + r, red, parity, dacc);
+            if (rs_li >= 0) {
+              cbar();     // the rows are final in global memory (st.cg); read them back with ld.cg
+              colscan_tile<kThreads, true>(d.gptr, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
+                                           rs_min, rs_max, rsx.dmin, rsx.dmax);
+            }
             mbar_arrive(ws.done(sidx));
           } else {
             // rows leave from the consumers' registers (`done` is arrived inside), or in place for the producer's bulk store
@@ -917,12 +984,12 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
             cle_tile_smem(c, P, in_mode, buf, d.gptr, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr,
                           ws.done(sidx));
             if (kTmaStore) {
-              if (d.kind == TK_BULK) {
-                fence_proxy_async_smem();          // my generic-proxy writes -> visible to the bulk store
-              } else {
-                cbar();
-                for (int i = ctid(); i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
-              }
+              if (rs_li >= 0 || d.kind != TK_BULK) cbar();      // every row of the tile is final in the stage
+              if (rs_li >= 0)
+                colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
+                                              rs_min, rs_max, rsx.dmin, rsx.dmax);
+              if (d.kind == TK_BULK) fence_proxy_async_smem();   // my generic-proxy writes -> visible to the bulk store
+              else for (int i = ctid(); i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
               mbar_arrive(ws.done(sidx));         // hand the tile back to the producer
             }
           }
@@ -932,6 +999,7 @@ k_cle_engine(float* arena, const DfqLayer* L, int nL, const DfqRelation* R, int 
 #endif
         }
 #undef DFQ_TT
+        rs_flush();
         flush();
         fence_proxy_async_all();   // this pass's plain row stores -> the next pass's bulk loads (async proxy)
         __threadfence();
@@ -1042,7 +1110,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
       const DfqLayer& l = layers[li];
       DFQ_REQUIRE(l.rel_in >= 0 || l.rel_out >= 0, "step layer without relation");
       t += pass_tiles(l);
-      if (l.rel_in >= 0 && l.col_mode == 2) rescan[p] = 1;
+      if (l.rel_in >= 0 && l.col_mode == 2 && !kFuseRescan) rescan[p] = 1;
     }
     max_tiles = std::max(max_tiles, t);
   }
@@ -1053,10 +1121,13 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   DFQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DFQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) { set_error("device does not support cooperative launch"); return DFQ_E_NOT_COOPERATIVE; }
-  // table cache for small models (see the kernel): decided before the occupancy query because it adds shared memory
-  const int n_entries_early = step_ptr[n_steps];
+  bool any_rescan = false;
+  for (int i = 0; i < n_layers; ++i) any_rescan |= (layers[i].rel_in >= 0 && layers[i].col_mode == 2);
+  int rs_cols = (kFuseRescan && any_rescan) ? kRescanCols : 0;
+  // table mirror for small models (see the kernel); its size must be known before the occupancy query
   size_t tbl_est = 0;
   {
+    const int n_entries_early = step_ptr[n_steps];
     int n_scan_est = 0;
     for (int i = 0; i < n_layers; ++i) n_scan_est += (layers[i].rel_in >= 0 && !(layers[i].flags & DFQ_LAYER_COLS_READY));
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -1064,7 +1135,8 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
               al(4 * n_steps) + al(8 * (n_entries_early + 1)) + al(8 * (n_scan_est + 1)) + al(4 * n_scan_est);
   }
   const bool cache_tables = tbl_est <= kTableCacheBytes;
-  const size_t dyn_smem = cache_tables ? ((WsPipe::smem_bytes() + 255) & ~(size_t)255) + tbl_est : WsPipe::smem_bytes();
+  const size_t dyn_smem = ((WsPipe::smem_bytes() + 15) & ~(size_t)15) + (size_t)kTeams * 2 * rs_cols * sizeof(float) +
+                          (cache_tables ? tbl_est : 0);
   DFQ_CUDA(cudaFuncSetAttribute(k_cle_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cle_engine, kCtaThreads, dyn_smem));
   if (per_sm < 1) { set_error("persistent kernel does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
@@ -1105,7 +1177,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   int tbl_bytes = cache_tables ? (int)tp.total : 0;
   if (cache_tables && tp.total != tbl_est) { set_error("internal: table pack size mismatch"); return DFQ_E_ARG; }
   void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS,
-                  &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups, &d_tbl, &tbl_bytes};
+                  &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups, &rs_cols, &d_tbl, &tbl_bytes};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kCtaThreads), args, dyn_smem, st));
   h_launch = ms_since(h0);
   CleCtl h;

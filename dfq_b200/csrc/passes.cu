@@ -314,7 +314,7 @@ __device__ __forceinline__ double bc_row(const float* __restrict__ row, int cols
 __global__ void __launch_bounds__(kThreads, kPipeCtas)
 k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __restrict__ B, int nB,
             const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits,
-            const long long* __restrict__ row_ptr, const long long* __restrict__ mm_ptr) {
+            const long long* __restrict__ row_ptr, const long long* __restrict__ mm_ptr, const int* __restrict__ level_local) {
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[2 * kWarps];
   __shared__ double dred[kWarps];
@@ -380,6 +380,10 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
 
   for (int lev = 0; lev < n_levels; ++lev) {
     // ---- E[x] of every layer of this level (dfq.py:228-278); one CTA per layer, terms in order ----
+    // A level of a few small layers (level_local: a serial model, one layer per level) skips this phase and its grid barrier:
+    // every CTA evaluates the recipe itself, straight into its shared-memory copy, when it reaches the layer below.
+    const bool local = level_local[lev] != 0;
+    if (!local) {
     for (int bi = level_ptr[lev] + blockIdx.x; bi < level_ptr[lev + 1]; bi += gridDim.x) {
       const DfqBcLayer b = B[bi];
       float* ex = arena + b.expect_off;
@@ -395,6 +399,7 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
       }
     }
     grid.sync();
+    }
     // ---- eps . E[x] per output row (dfq.py:216-219,281-293): rows streamed through the pipe, read only ---------
     MatIter<BcGeo> it;
     it.start(row_ptr, level_ptr[lev], level_ptr[lev + 1], BcGeo{arena, L, B});
@@ -413,7 +418,18 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
         so = l.rows / (b.expect_len / l.cols);
         ex_cached = (b.expect_len <= kExpectCache);
         __syncthreads();
-        if (ex_cached) {
+        if (local) {             // host guarantees expect_len <= kExpectCache for every layer of a local level
+          for (int ti = b.term_begin; ti < b.term_end; ++ti) {
+            const DfqExpectTerm t = T[ti];
+            for (int ch = threadIdx.x; ch < t.n; ch += kThreads) {
+              const float fb = __ldcg(arena + t.bn_b_off + ch);
+              const float v = t.relu ? relu_gauss_mean(__ldcg(arena + t.bn_w_off + ch), fb) : fb;
+              float* dst = s_ex + t.dst_off + ch;
+              *dst = t.accumulate ? __fadd_rn(*dst, v) : v;
+            }
+            __syncthreads();
+          }
+        } else if (ex_cached) {
           for (int j = threadIdx.x; j < b.expect_len; j += kThreads) s_ex[j] = __ldcg(arena + b.expect_off + j);
           __syncthreads();
         }
@@ -584,6 +600,12 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
     mm_ptr[i + 1] = mm_ptr[i] + (b.n_col > 0 ? 0 : pipe_tiles(l.rows, l.cols * l.kk));
   }
   max_tiles = std::max<int64_t>(max_tiles, row_ptr[n_bc]);
+  std::vector<int32_t> level_local(n_levels, 0);
+  for (int lv = 0; lv < n_levels; ++lv) {
+    bool ok = (level_ptr[lv + 1] - level_ptr[lv]) <= 4;
+    for (int i = level_ptr[lv]; ok && i < level_ptr[lv + 1]; ++i) ok = bc[i].expect_len <= kExpectCache;
+    level_local[lv] = ok ? 1 : 0;
+  }
   int grid, rc;
   const size_t dyn = RowPipe::smem_bytes();
   DFQ_CUDA(cudaFuncSetAttribute(k_bc_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -591,10 +613,12 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   TablePack tp;
   const int iL = tp.add(layers, n_layers), iB = tp.add(bc, n_bc), iT = tp.add(terms, n_terms);
   const int iLP = tp.add(level_ptr, n_levels + 1), iRP = tp.add(row_ptr.data(), n_bc + 1), iMP = tp.add(mm_ptr.data(), n_bc + 1);
+  const int iLL = tp.add(level_local.data(), n_levels);
   if ((rc = tp.upload(st))) return rc;
   DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqBcLayer* dB = tp.ptr<DfqBcLayer>(iB); DfqExpectTerm* dT = tp.ptr<DfqExpectTerm>(iT);
   int32_t* dLP = tp.ptr<int32_t>(iLP); long long* dRP = tp.ptr<long long>(iRP); long long* dMP = tp.ptr<long long>(iMP);
-  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP, &dMP};
+  int32_t* dLL = tp.ptr<int32_t>(iLL);
+  void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP, &dMP, &dLL};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, dyn, st));
   tp.release(st);
   return 0;
