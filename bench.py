@@ -87,9 +87,9 @@ class ClockSampler(threading.Thread):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_cle_engine from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full_1024layers.md: 24.264 GB read + 19.627 GB written at 1024 pairs, 2 sweeps).  The kernel's traffic is linear
+# (profiles/r1_ncu_full_1024layers.md: 19.407 GB read + 19.548 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The kernel's traffic is linear
 # in the number of pairs (every block is identical), so the figure is scaled to the benched size; None for other sweep counts.
-NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 43.891e9
+NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.955e9
 NCU_TRAFFIC_SOURCE = "ncu --set full capture at 1024 pairs (profiles/r1_ncu_full_1024layers.md), scaled linearly to the benched pairs"
 
 
@@ -320,8 +320,8 @@ def run_b200(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_cle_engine", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(layers, res.n_sweeps), "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_launch": cle_bytes, "ms_per_launch": ms_cle,
-                "whole_step": {"algorithmic_bytes": (28.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers,
-                               "GB/s": (28.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers / (ms_step * 1e-3) / 1e9}}
+                "whole_step": {"algorithmic_bytes": (26.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers,
+                               "GB/s": (26.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers / (ms_step * 1e-3) / 1e9}}
 
     # ---- end to end with host buffers -----------------------------------------------------------------------------
     e2e = None

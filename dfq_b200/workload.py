@@ -172,7 +172,7 @@ class DeviceStack:
 
     Pipeline per calibration step (the BASELINE metric's unit of work, per Conv/BN pair):
       BN fold (8N B) -> equalization to convergence (8N B per sweep, 2 sweeps) -> bias correction of the second
-      conv (4N B read twice = 4N B per pair on average) [-> 8-bit weight fake-quant (8N+4N B)]
+      conv (4N B read once - its range comes from the equalization's column extrema - = 2N B per pair on average) [-> 8-bit weight fake-quant (8N+4N B)]
     """
 
     def __init__(self, sess, n_blocks: int, channels: int = 512, k: int = 3, seed: int = 1234, quantize: bool = False):
@@ -246,7 +246,9 @@ class DeviceStack:
 
     @property
     def launches_per_step(self) -> int:
-        return 3 + (3 if self.quant_plan is not None else 0)
+        """Kernels of this library per step: column-range reset + fold, equalization engine, correction engine
+        [+ range init, min/max, quantize]."""
+        return 4 + (3 if self.quant_plan is not None else 0)
 
 
 class HostStackCalibrator:
