@@ -177,3 +177,25 @@ def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8,
             S = S_all[i, :chan[i]].clone()
             rr.set_scale_vec(S if graph[rr.get_idxs()[0]].weight.is_cuda else S.cpu())
         return dict(owner=owner, chains=chains, sweeps=sweeps)
+
+
+def sync_observers(model: nn.Module, group=None) -> int:
+    """Data-parallel `update_quant_range` (improve_dfq.py:280-300): every rank drives its QuantMeasure observers over ITS share
+    of the distilled batches in `update_stat` mode (running_max = max(running_max, stat), quantize.py:103-107), then calls
+    this once: two all-reduces (MIN over every running_min, MAX over every running_max, 2 floats per observer) leave all
+    ranks with the ranges a single process would have reached over all batches - max/min are associative, so the result does
+    not depend on how whole batches were dealt to the ranks ("replicas only").  Returns the number of observers."""
+    from .utils.quantize import QuantMeasure
+    obs = [m for m in model.modules() if isinstance(m, QuantMeasure)]
+    if not obs or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return len(obs)
+    with torch.no_grad():
+        dev = obs[0].running_min.device
+        mn = torch.cat([m.running_min.reshape(1).to(dev) for m in obs])
+        mx = torch.cat([m.running_max.reshape(1).to(dev) for m in obs])
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        for i, m in enumerate(obs):
+            m.running_min.reshape(1).copy_(mn[i:i + 1])
+            m.running_max.reshape(1).copy_(mx[i:i + 1])
+    return len(obs)

@@ -87,3 +87,40 @@ def test_partition_and_chains_are_deterministic():
     # dfq.py:81-115 replay: stops when diff <= thres or after converge_count stagnant sweeps
     assert _replay_exit_rule([1.0, 0.5, 1e-8], 2e-7, 20) == 3
     assert _replay_exit_rule([1.0] * 30, 2e-7, 3) == 4
+
+
+def _observer_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import torch.nn as nn
+    import fakelib
+    from dfq_b200 import dist as ddist
+    from dfq_b200.utils.quantize import QuantMeasure
+    torch.set_num_threads(1)
+    fakelib.install_plain()
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        model = nn.Sequential(QuantMeasure(True, 8), nn.ReLU(), nn.Sequential(QuantMeasure(True, 8), QuantMeasure(True, 8)))
+        obs = [m for m in model.modules() if isinstance(m, QuantMeasure)]
+        g = torch.Generator().manual_seed(100 + rank)          # what this rank's share of the batches left behind
+        for m in obs:
+            m.running_min.fill_(float(-torch.rand(1, generator=g)))
+            m.running_max.fill_(float(torch.rand(1, generator=g)))
+        before = np.array([[float(m.running_min), float(m.running_max)] for m in obs])
+        n = ddist.sync_observers(model)
+        after = np.array([[float(m.running_min), float(m.running_max)] for m in obs])
+        np.savez(os.path.join(out_dir, "obs%d.npz" % rank), before=before, after=after, n=n)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_observer_sync(tmp_path):
+    """sync_observers: every rank ends with min over ranks of running_min and max over ranks of running_max of every
+    QuantMeasure (what one process would have reached over all batches in update_stat mode, quantize.py:103-107)."""
+    port = 29500 + (os.getpid() % 2000) + 23
+    mp.spawn(_observer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "obs0.npz"), np.load(tmp_path / "obs1.npz")
+    assert int(r0["n"]) == 3 and int(r1["n"]) == 3
+    want = np.stack([np.minimum(r0["before"][:, 0], r1["before"][:, 0]), np.maximum(r0["before"][:, 1], r1["before"][:, 1])], axis=1)
+    assert np.array_equal(r0["after"], want) and np.array_equal(r1["after"], want)
