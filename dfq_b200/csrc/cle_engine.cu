@@ -17,7 +17,8 @@
 //   * column ranges needed by the *next* sweep are not re-read: rounding is monotone, so after a
 //     pure column scaling  max(fl(v*a)) = fl(max(v)*a)  for a > 0 (likewise min), and the running
 //     column extrema are updated analytically ("derived").  Only general middle layers (both
-//     column- and row-scaled with cols > 1) are re-scanned.
+//     column- and row-scaled with cols > 1) need fresh extrema every sweep, accumulated from the
+//     rescaled tile while it still sits in shared memory.
 //   * the step barrier between chain positions is a grid barrier of the persistent kernel.
 #include <cooperative_groups.h>
 
@@ -70,7 +71,6 @@ __device__ __forceinline__ void cbar() {
   if (kTeams == 1) asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
   else asm volatile("bar.sync %0, %1;" ::"r"(1 + team()), "n"(kThreads) : "memory");
 }
-constexpr int kScanRows = 32;      // rows per column-scan tile
 #ifndef DFQ_INV_CACHE
 #define DFQ_INV_CACHE 2044
 #endif
@@ -104,10 +104,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 // pass tiles: contiguous chunks of rows moved by the RowPipe (rowpipe.cuh)
 __host__ __device__ inline int pass_tiles(const DfqLayer& l) { return pipe_tiles(l.rows, l.cols * l.kk); }
-__host__ __device__ inline int scan_tiles(int G, int go) {
-  return G * ((go + kScanRows - 1) / kScanRows);
-}
-
 // Everything a row pass needs to know about its layer; uniform across the CTA.
 struct RowCtx {
   float* w;
@@ -256,36 +252,29 @@ __device__ __forceinline__ float in_scale1(float t, int e, const float* __restri
 
 // float4 slots a thread keeps in registers between the range reduction and the rescale (kThreads * kRowRegs * 4 >= kStageFloats)
 constexpr int kRowRegs = (kStageFloats / 4 + kThreads - 1) / kThreads;
-// How a rescaled row leaves the SM:  1 = written back into its stage, the producer warp bulk-stores the tile (TMA);
-// 0 = straight from the consumers' registers with streaming stores (the stage is released as soon as the row is in registers).
-#ifndef DFQ_TMA_STORE
-#define DFQ_TMA_STORE 1
-#endif
-constexpr bool kTmaStore = DFQ_TMA_STORE != 0;
-// General middle layers (row- AND column-scaled, cols > 1) need their column extrema recomputed every sweep.  With the bulk
-// store the rescaled tile sits in its stage anyway: the extrema are accumulated right there (no second read of the layer, no
-// extra grid-wide phase).  Without it (DFQ_TMA_STORE=0) a separate scan phase follows the layer's pass.
-constexpr bool kFuseRescan = kTmaStore;
+// A rescaled row is written back into its stage and the producer warp bulk-stores the tile (TMA).  (Measured alternative:
+// straight from the consumers' registers with st.global - stage released right after the range reduction - was 25-40 %
+// slower on the stack with every cache policy tried)
+// General middle layers (row- AND column-scaled, cols > 1) need their column extrema recomputed every sweep: the rescaled
+// tile sits in its stage anyway, so the extrema are accumulated right there (no second read of the layer, no extra
+// grid-wide phase).
 constexpr int kRescanCols = 1024;   // columns a team accumulates in shared memory (more: global atomics)
 constexpr size_t kTableCacheBytes = 9 * 1024;   // descriptor tables of a model this small are mirrored in shared memory
 constexpr int TK_END = 3;   // sentinel tile: the pass is over for this CTA (the consumers keep no iterator of their own)
 static_assert(kThreads * kRowRegs * 4 >= kStageFloats, "a single-row tile must fit the consumers' registers");
 
-// One row resident in shared memory: [range reduction -> s] (HAS_OUT), rescale, accumulate |new - old|.  The rescaled row goes
-// back into its stage for the producer's bulk store (default), or straight to global memory (DFQ_TMA_STORE=0).  A row with a
-// reduction is read from shared memory ONCE when it fits the registers (always for the CTA-wide single-row tiles).
+// One row resident in shared memory: [range reduction -> s] (HAS_OUT), rescale IN PLACE, accumulate |new - old|.  A row with
+// a reduction is read from shared memory ONCE when it fits the registers (always for the CTA-wide single-row tiles).
 // `in`: what the row needs from global memory, fetched ahead by the caller; the scale pair comes back in *s_out / *inv_out
-// and the caller does (or delegates) the per-channel bookkeeping.  `done`: the stage's consumer->producer barrier, arrived as
-// soon as this thread no longer needs the stage (nullptr: the caller arrives).
+// and the caller does (or delegates) the per-channel bookkeeping.
 template <int TPR, int MODE, bool HAS_OUT>
-__device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams P, float* __restrict__ row,
-                                             float* __restrict__ grow, int o, int lane, const float* __restrict__ s_inv,
-                                             float* red, int& parity, double& dacc, const RowIn& in, float* s_out,
-                                             float* inv_out, uint64_t* done) {
+__device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams P, float* __restrict__ row, int o, int lane,
+                                             const float* __restrict__ s_inv, float* red, int& parity, double& dacc,
+                                             const RowIn& in, float* s_out, float* inv_out) {
   const int n = c.row_len, kk = c.kk;
-  const bool vec = ((n & 3) == 0) && (kTmaStore || (((uintptr_t)grow) & 15) == 0);
-  auto put4 = [&](int i4, const float4& t) { if (kTmaStore) ((float4*)row)[i4] = t; else stg_stream((float4*)grow + i4, t); };
-  auto put1 = [&](int e, float t) { if (kTmaStore) row[e] = t; else stg_stream1(grow + e, t); };
+  const bool vec = ((n & 3) == 0);
+  auto put4 = [&](int i4, const float4& t) { ((float4*)row)[i4] = t; };
+  auto put1 = [&](int e, float t) { row[e] = t; };
   const int n4 = n >> 2;
   const double inv_n = c.inv_n;
   const float* inv = nullptr;
@@ -301,9 +290,9 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
     *s_out = s; *inv_out = iv;
   };
   float dsum = 0.f;
-  // a row that only gets its columns scaled (no reduction to wait for) streams through the in-place loop further down when
-  // the tile leaves by bulk store: holding it in registers buys nothing there and measured ~12% slower
-  if (vec && n4 <= TPR * kRowRegs && (HAS_OUT || !kTmaStore)) {
+  // a row that only gets its columns scaled (no reduction to wait for) streams through the in-place loop further down:
+  // holding it in registers buys nothing there and measured ~12% slower
+  if (vec && n4 <= TPR * kRowRegs && HAS_OUT) {
     const float4* r4 = (const float4*)row;
     float4 v[kRowRegs];
 #pragma unroll
@@ -323,7 +312,6 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
         }
       }
       solve(mn, mx);
-      if (done) mbar_arrive(done);        // the row lives in registers: the stage can be refilled while it is rescaled
     }
 #pragma unroll
     for (int k = 0; k < kRowRegs; ++k) {
@@ -336,7 +324,6 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
                 fabsf(__fsub_rn(t.w, v[k].w));
       }
     }
-    if (!HAS_OUT && done) mbar_arrive(done);
   } else if (vec) {
     const float4* r4 = (const float4*)row;
     if (HAS_OUT) {
@@ -357,7 +344,6 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
       put4(i4, t);
       dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
     }
-    if (done) mbar_arrive(done);
   } else {
     if (HAS_OUT) {
       float mn = DFQ_INF, mx = -DFQ_INF;
@@ -374,26 +360,18 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
       put1(e, t);
       dsum += fabsf(__fsub_rn(t, v));
     }
-    if (done) mbar_arrive(done);
   }
   dacc += (double)dsum * inv_n;
 }
 
-// A tile of whole rows in shared memory -> rescaled rows (in place for the bulk store, or in global memory at `g`);
-// with DFQ_TMA_STORE=0 every consumer thread arrives on `done` in here.
+// A tile of whole rows in shared memory, rescaled in place.
 //   one row   : the whole team works on it; its global-memory inputs arrive in the stage mailbox and the bookkeeping is left
 //               to the producer warp (mailbox again)
 //   many rows : a warp per row, 32 rows per batch -- lane j fetches row j's inputs before the batch and does row j's
 //               bookkeeping after it, so a batch pays TWO global-memory latencies instead of two per row
-#ifdef DFQ_NOINLINE_TILE
-#define DFQ_TILE_INLINE __noinline__
-#else
-#define DFQ_TILE_INLINE __forceinline__
-#endif
 template <int MODE, bool HAS_OUT>
-__device__ DFQ_TILE_INLINE void cle_tile_rows(const RowCtx& c, const DfqCleParams& P, float* buf, float* g, int row0,
-                                              int nrows, const float* s_inv, float* red, int& parity, double& dacc,
-                                              StagePub* pub, uint64_t* done) {
+__device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParams& P, float* buf, int row0, int nrows,
+                                              const float* s_inv, float* red, int& parity, double& dacc, StagePub* pub) {
   const int warp = ctid() >> 5, lane = ctid() & 31;
   if (nrows == 1) {
     RowIn in;
@@ -402,8 +380,7 @@ __device__ DFQ_TILE_INLINE void cle_tile_rows(const RowCtx& c, const DfqCleParam
                           if (P.apply_only) in.s_given = __ldcg(c.s_acc + row0); }
     else in = fetch_row_in(c, P, row0, MODE == IN_UNIFORM);
     float sv = 1.f, iv = 1.f;
-    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, g, row0, ctid(), s_inv, red, parity, dacc, in, &sv, &iv,
-                                          kTmaStore ? nullptr : done);
+    cle_row_smem<kThreads, MODE, HAS_OUT>(c, P, buf, row0, ctid(), s_inv, red, parity, dacc, in, &sv, &iv);
     if (HAS_OUT && ctid() == 0) {
       if (pub) { pub->s = sv; pub->inv = iv; }
       else publish_row(c, P, row0, sv, iv, in.cmn, in.cmx);
@@ -424,24 +401,21 @@ __device__ DFQ_TILE_INLINE void cle_tile_rows(const RowCtx& c, const DfqCleParam
         in.cmn = __shfl_sync(0xffffffffu, mine_in.cmn, j); in.cmx = __shfl_sync(0xffffffffu, mine_in.cmx, j);
         in.u = __shfl_sync(0xffffffffu, mine_in.u, j); in.s_given = __shfl_sync(0xffffffffu, mine_in.s_given, j);
         float sv = 1.f, iv = 1.f;
-        cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, g + (size_t)r * row_len, row0 + r, lane, s_inv, red,
-                                        parity, dacc, in, &sv, &iv, nullptr);
+        cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, row0 + r, lane, s_inv, red, parity, dacc, in, &sv, &iv);
         if (lane == j) { ks = sv; kinv = iv; }
       }
       if (HAS_OUT && il < mine) publish_row(c, P, ol, ks, kinv, mine_in.cmn, mine_in.cmx);
     }
-    if (!kTmaStore) mbar_arrive(done);
   }
 }
 
-__device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParams P, int in_mode, float* buf, float* g,
-                                              int row0, int nrows, const float* s_inv, float* red, int& parity, double& dacc,
-                                              StagePub* pub, uint64_t* done) {
-#define DFQ_TILE(M)                                                                                            \
-  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, g, row0, nrows, s_inv, red, parity, dacc, pub, done);       \
-  else cle_tile_rows<M, false>(c, P, buf, g, row0, nrows, s_inv, red, parity, dacc, pub, done);
+__device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParams P, int in_mode, float* buf, int row0, int nrows,
+                                              const float* s_inv, float* red, int& parity, double& dacc, StagePub* pub) {
+#define DFQ_TILE(M)                                                                            \
+  if (c.has_out) cle_tile_rows<M, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub); \
+  else cle_tile_rows<M, false>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub);
   switch (in_mode) {
-    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, g, row0, nrows, s_inv, red, parity, dacc, pub, done); break;
+    case IN_NONE: cle_tile_rows<IN_NONE, true>(c, P, buf, row0, nrows, s_inv, red, parity, dacc, pub); break;
     case IN_UNIFORM: DFQ_TILE(IN_UNIFORM) break;
     case IN_KK1: DFQ_TILE(IN_KK1) break;
     case IN_KK9: DFQ_TILE(IN_KK9) break;
@@ -519,53 +493,6 @@ __device__ __forceinline__ void make_ctx(RowCtx& c, float* arena, const DfqLayer
     c.s_acc = arena + r.s_acc_off;
     c.bnw = r.bn_w_off >= 0 ? arena + r.bn_w_off : nullptr;
     c.bnb = r.bn_b_off >= 0 ? arena + r.bn_b_off : nullptr;
-  }
-}
-
-// Column extrema of rows [r0, r1) of group g of layer l, folded into dst (global float atomics).
-__device__ void scan_cols_tile(const float* w, int J, int kk, int g, int gi, int r0, int r1,
-                               float* dmin, float* dmax, float* smin, float* smax) {
-  const int row_len = J * kk;
-  const bool use_smem = (J <= kScanCols);
-  if (use_smem) {
-    for (int j = ctid(); j < J; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
-    cbar();
-  }
-  for (int p = ctid(); p < row_len; p += kThreads) {
-    float mn = DFQ_INF, mx = -DFQ_INF;
-    const float* q = w + (size_t)r0 * row_len + p;
-#pragma unroll 8
-    for (int r = r0; r < r1; ++r, q += row_len) {
-      const float v = ldg_stream1(q);
-      mn = fminf(mn, v); mx = fmaxf(mx, v);
-    }
-    const int j = col_of(p, kk);
-    if (use_smem) { atomic_min_f(smin + j, mn); atomic_max_f(smax + j, mx); }
-    else { atomic_min_f(dmin + g * gi + j, mn); atomic_max_f(dmax + g * gi + j, mx); }
-  }
-  if (use_smem) {
-    cbar();
-    for (int j = ctid(); j < J; j += kThreads) {
-      atomic_min_f(dmin + g * gi + j, smin[j]);
-      atomic_max_f(dmax + g * gi + j, smax[j]);
-    }
-    cbar();
-  }
-}
-
-// scan tiles [t0, t1) of layer li (tile = 32 rows of one group)
-__device__ __forceinline__ void scan_layer(float* arena, const DfqLayer* L, const DfqRelation* R, int li,
-                                           int buf, long long t0, long long t1, float* smin, float* smax) {
-  const DfqLayer l = L[li];
-  const DfqRelation r = R[l.rel_in];
-  const int nb = (r.go + kScanRows - 1) / kScanRows;
-  for (long long t = t0; t < t1; ++t) {
-    const int g = (int)(t / nb), b = (int)(t - (long long)g * nb);
-    const int r0 = g * r.go + b * kScanRows;
-    const int r1 = min(r0 + kScanRows, (g + 1) * r.go);
-    scan_cols_tile(arena + l.w_off, l.cols, l.kk, g, r.gi, r0, r1,
-                   arena + l.cmin_off + (size_t)buf * r.channels,
-                   arena + l.cmax_off + (size_t)buf * r.channels, smin, smax);
   }
 }
 
@@ -690,7 +617,7 @@ __device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, cons
         const TileDesc d = *ws.desc(sr);
         const StagePub pb = *ws.pub(sr);
         __syncwarp();                                                        // everyone holds a copy before the stage is recycled
-        if (kTmaStore && lane == 0 && d.kind == TK_BULK) {
+        if (lane == 0 && d.kind == TK_BULK) {
           bulk_s2g(d.gptr, ws.stage(sr), (uint32_t)d.floats * 4u);
           bulk_commit();
           bulk_wait_read<0>();                                               // the stage may be overwritten now
@@ -731,7 +658,7 @@ __device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, cons
     }
     __syncwarp();
   }
-  if (kTmaStore && lane == 0) {
+  if (lane == 0) {
     bulk_wait_all();
     fence_proxy_async_all();
   }
@@ -743,7 +670,7 @@ __device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, cons
 __global__ void __launch_bounds__(kCtaThreads, kCleCtas)
 k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRelation* __restrict__ gR, int nR,
              const int* __restrict__ g_step_ptr, const int* __restrict__ g_step_layers, int n_steps,
-             const int* __restrict__ g_step_rescan, const long long* __restrict__ g_pass_ptr,
+             const long long* __restrict__ g_pass_ptr,
              const long long* __restrict__ g_scan_ptr, const int* __restrict__ g_scan_layers, int n_scan,
              DfqCleParams P, CleCtl* ctl, GroupState* G, int nG, int rs_cols, const unsigned char* tbl, int tbl_bytes) {
   cg::grid_group grid = cg::this_grid();
@@ -785,7 +712,6 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
   const DfqRelation* R = DFQ_TAB(DfqRelation, gR);
   const int* step_ptr = DFQ_TAB(int, g_step_ptr);
   const int* step_layers = DFQ_TAB(int, g_step_layers);
-  const int* step_rescan = DFQ_TAB(int, g_step_rescan);
   const long long* pass_ptr = DFQ_TAB(long long, g_pass_ptr);
   const long long* scan_ptr = DFQ_TAB(long long, g_scan_ptr);
   const int* scan_layers = DFQ_TAB(int, g_scan_layers);
@@ -849,15 +775,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
           dmin = arena + l.cmin_off; dmax = arena + l.cmax_off;    // buffer 0
         }
         if (d.kind == TK_DIRECT) {   // a row longer than a stage: straight from global memory
-          flush();
-          for (int r = d.row0; r < d.row0 + d.nrows; ++r) {
-            const int g = r / go;
-            scan_cols_tile(arena + L[cur_li].w_off, J, kk, g, gi, r, r + 1, dmin, dmax, smin, smax);
-          }
-          if (J <= kScanCols) {      // scan_cols_tile leaves its scratch dirty
-            for (int j = ctid(); j < J; j += kThreads) { smin[j] = DFQ_INF; smax[j] = -DFQ_INF; }
-            cbar();
-          }
+          colscan_tile<kThreads, true>(d.gptr, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
         } else {
           colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
         }
@@ -945,27 +863,23 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
               if (ctid() == 0) s_inv[sctx.cols] = 1.f;
               cbar();
             }
-            if (kFuseRescan) {
-              rs_flush();
-              const DfqLayer l = L[cur_li];
-              if (l.col_mode == 2 && l.rel_in >= 0) {       // accumulate into the NEXT sweep's buffer, reset one step ago
-                rs_li = cur_li;
-                if (ctid() == 0) {
-                  const DfqRelation r = R[l.rel_in];
-                  rsx.nch = r.channels; rsx.go = r.go; rsx.gi = r.gi;
-                  rsx.single = (r.groups == 1); rsx.smem = (r.channels <= rs_cols);
-                  rsx.own = (pipe_rows_per_tile(l.cols * l.kk) == 1);
-                  rsx.dmin = arena + l.cmin_off + (size_t)((sweep & 1) ^ 1) * r.channels;
-                  rsx.dmax = arena + l.cmax_off + (size_t)((sweep & 1) ^ 1) * r.channels;
-                }
-                cbar();
+            rs_flush();
+            const DfqLayer l = L[cur_li];
+            if (l.col_mode == 2 && l.rel_in >= 0) {       // accumulate into the NEXT sweep's buffer, reset one step ago
+              rs_li = cur_li;
+              if (ctid() == 0) {
+                const DfqRelation r = R[l.rel_in];
+                rsx.nch = r.channels; rsx.go = r.go; rsx.gi = r.gi;
+                rsx.single = (r.groups == 1); rsx.smem = (r.channels <= rs_cols);
+                rsx.own = (pipe_rows_per_tile(l.cols * l.kk) == 1);
+                rsx.dmin = arena + l.cmin_off + (size_t)((sweep & 1) ^ 1) * r.channels;
+                rsx.dmax = arena + l.cmax_off + (size_t)((sweep & 1) ^ 1) * r.channels;
               }
-            } else if (L[cur_li].col_mode == 2 && L[cur_li].rel_in >= 0 && d.row0 == 0) {
-              reset_cols(arena, L[cur_li], R[L[cur_li].rel_in], (sweep & 1) ^ 1);
+              cbar();
             }
           }
           // the re-scanned successor's next-sweep buffer is reset HERE, one step (= one grid barrier) before its pass fills it
-          if (kFuseRescan && d.row0 == 0 && sctx.has_out) {
+          if (d.row0 == 0 && sctx.has_out) {
             const DfqRelation ro = R[L[cur_li].rel_out];
             if (L[ro.second].col_mode == 2) reset_cols(arena, L[ro.second], ro, (sweep & 1) ^ 1);
           }
@@ -979,19 +893,15 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
             }
             mbar_arrive(ws.done(sidx));
           } else {
-            // rows leave from the consumers' registers (`done` is arrived inside), or in place for the producer's bulk store
             StagePub* pub = ws.pub(sidx);
-            cle_tile_smem(c, P, in_mode, buf, d.gptr, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr,
-                          ws.done(sidx));
-            if (kTmaStore) {
-              if (rs_li >= 0 || d.kind != TK_BULK) cbar();      // every row of the tile is final in the stage
-              if (rs_li >= 0)
-                colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
-                                              rs_min, rs_max, rsx.dmin, rsx.dmax);
-              if (d.kind == TK_BULK) fence_proxy_async_smem();   // my generic-proxy writes -> visible to the bulk store
-              else for (int i = ctid(); i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
-              mbar_arrive(ws.done(sidx));         // hand the tile back to the producer
-            }
+            cle_tile_smem(c, P, in_mode, buf, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr);
+            if (rs_li >= 0 || d.kind != TK_BULK) cbar();      // every row of the tile is final in the stage
+            if (rs_li >= 0)
+              colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
+                                            rs_min, rs_max, rsx.dmin, rsx.dmax);
+            if (d.kind == TK_BULK) fence_proxy_async_smem();   // my generic-proxy writes -> visible to the bulk store
+            else for (int i = ctid(); i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
+            mbar_arrive(ws.done(sidx));         // hand the tile back to the producer
           }
           DFQ_TT(2);
 #ifdef DFQ_TILE_TRACE
@@ -1006,25 +916,6 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
       }
       grid.sync();
       mark();
-      if (step_rescan[p]) {   // general middle layers of this step: round-robin over their scan tiles
-        if (!producer) {
-          long long sbase = 0;
-          for (int q = step_ptr[p]; q < step_ptr[p + 1]; ++q) {
-            const int li = step_layers[q];
-            if (L[li].col_mode == 2 && L[li].rel_in >= 0 && !*((volatile int*)&G[L[li].group].done)) {
-              const DfqRelation r = R[L[li].rel_in];
-              const long long nt = scan_tiles(r.groups, r.go);
-              long long first = ((long long)vblock() - sbase) % (long long)vgrid();
-              if (first < 0) first += vgrid();
-              for (long long t = first; t < nt; t += vgrid())
-                scan_layer(arena, L, R, li, (sweep & 1) ^ 1, t, t + 1, smin, smax);
-              sbase += nt;
-            }
-          }
-        }
-        grid.sync();
-        mark();
-      }
     }
     // ---- exit rule of dfq.py:105-115, one thread per group ------------------------------------------------
     const int n = sweep + 1;
@@ -1074,7 +965,6 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
 
   // ---- validate descriptors, find the widest phase -----------------------------------------------
   int64_t max_tiles = 1;
-  std::vector<int32_t> rescan(n_steps, 0);
   for (int i = 0; i < n_rels; ++i) {
     const DfqRelation& r = rels[i];
     DFQ_REQUIRE(r.first >= 0 && r.first < n_layers && r.second >= 0 && r.second < n_layers, "relation layer index");
@@ -1110,7 +1000,6 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
       const DfqLayer& l = layers[li];
       DFQ_REQUIRE(l.rel_in >= 0 || l.rel_out >= 0, "step layer without relation");
       t += pass_tiles(l);
-      if (l.rel_in >= 0 && l.col_mode == 2 && !kFuseRescan) rescan[p] = 1;
     }
     max_tiles = std::max(max_tiles, t);
   }
@@ -1123,7 +1012,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   if (!coop) { set_error("device does not support cooperative launch"); return DFQ_E_NOT_COOPERATIVE; }
   bool any_rescan = false;
   for (int i = 0; i < n_layers; ++i) any_rescan |= (layers[i].rel_in >= 0 && layers[i].col_mode == 2);
-  int rs_cols = (kFuseRescan && any_rescan) ? kRescanCols : 0;
+  int rs_cols = any_rescan ? kRescanCols : 0;
   // table mirror for small models (see the kernel); its size must be known before the occupancy query
   size_t tbl_est = 0;
   {
@@ -1132,7 +1021,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     for (int i = 0; i < n_layers; ++i) n_scan_est += (layers[i].rel_in >= 0 && !(layers[i].flags & DFQ_LAYER_COLS_READY));
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     tbl_est = al(sizeof(DfqLayer) * n_layers) + al(sizeof(DfqRelation) * n_rels) + al(4 * (n_steps + 1)) + al(4 * n_entries_early) +
-              al(4 * n_steps) + al(8 * (n_entries_early + 1)) + al(8 * (n_scan_est + 1)) + al(4 * n_scan_est);
+              al(8 * (n_entries_early + 1)) + al(8 * (n_scan_est + 1)) + al(4 * n_scan_est);
   }
   const bool cache_tables = tbl_est <= kTableCacheBytes;
   const size_t dyn_smem = ((WsPipe::smem_bytes() + 15) & ~(size_t)15) + (size_t)kTeams * 2 * rs_cols * sizeof(float) +
@@ -1157,13 +1046,13 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   int n_scan = (int)scan_layers.size();
   TablePack tp;
   const int iL = tp.add(layers, n_layers), iR = tp.add(rels, n_rels), iSP = tp.add(step_ptr, n_steps + 1);
-  const int iSL = tp.add(step_layers, n_entries), iRS = tp.add(rescan.data(), n_steps);
+  const int iSL = tp.add(step_layers, n_entries);
   const int iPP = tp.add(pass_ptr.data(), n_entries + 1), iSCP = tp.add(scan_ptr.data(), n_scan + 1);
   const int iSCL = tp.add(scan_layers.data(), n_scan);
   int rc;
   if ((rc = tp.upload(st))) return rc;
   DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqRelation* dR = tp.ptr<DfqRelation>(iR);
-  int32_t *dSP = tp.ptr<int32_t>(iSP), *dSL = tp.ptr<int32_t>(iSL), *dRS = tp.ptr<int32_t>(iRS), *dSCL = tp.ptr<int32_t>(iSCL);
+  int32_t *dSP = tp.ptr<int32_t>(iSP), *dSL = tp.ptr<int32_t>(iSL), *dSCL = tp.ptr<int32_t>(iSCL);
   long long *dPP = tp.ptr<long long>(iPP), *dSCP = tp.ptr<long long>(iSCP);
   CleCtl* dctl = nullptr;
   GroupState* dG = nullptr;
@@ -1176,7 +1065,7 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   const unsigned char* d_tbl = tp.dev;
   int tbl_bytes = cache_tables ? (int)tp.total : 0;
   if (cache_tables && tp.total != tbl_est) { set_error("internal: table pack size mismatch"); return DFQ_E_ARG; }
-  void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps, &dRS,
+  void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, (void*)&n_steps,
                   &dPP, &dSCP, &dSCL, (void*)&n_scan, &P, &dctl, &dG, (void*)&n_groups, &rs_cols, &d_tbl, &tbl_bytes};
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_engine, dim3(grid), dim3(kCtaThreads), args, dyn_smem, st));
   h_launch = ms_since(h0);
