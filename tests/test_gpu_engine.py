@@ -358,3 +358,41 @@ def test_fused_fold_scan_and_range_hints_equal_the_unfused_calls(shapes):
         assert np.array_equal(x.numpy(), y.numpy())
     for x, y in zip(fb_a, fb_b):
         assert np.array_equal(x, y)
+
+
+def test_bias_correction_codes_at_rounding_boundaries_are_the_references():
+    """The correction's quantizer decides most codes with a reciprocal multiplication and re-does the IEEE division only near
+    half-integers (csrc/common.cuh fake_quant_div_guarded).  Weights placed ON and within a few ulps of every rounding
+    boundary of the 8-bit grid must still give the reference's codes: with E[x] = 1 the row's delta is sum(eps) in fp64, so a
+    single wrong code shows as an error of one quantization step."""
+    from dfq_b200.engine import Session
+    rng = np.random.default_rng(7)
+    lo, hi = np.float32(-1.3717), np.float32(2.0461)
+    scale = (float(hi) - float(lo)) / 255.0
+    vals = []
+    for k in range(255):
+        b = np.float32(float(lo) + (k + 0.5) * scale)          # t/scale ~ k + 0.5
+        for d in range(-4, 5):
+            v = b
+            for _ in range(abs(d)):
+                v = np.nextafter(v, np.float32(np.inf if d > 0 else -np.inf), dtype=np.float32)
+            vals.append(v)
+    vals = np.array(vals, np.float32)
+    cols = 768
+    rows = 3 * ((vals.size + cols - 1) // cols)
+    w = rng.uniform(float(lo), float(hi), size=(rows, cols)).astype(np.float32)
+    w.reshape(-1)[:vals.size] = vals
+    w.reshape(-1)[vals.size] = lo; w.reshape(-1)[vals.size + 1] = hi      # pin the tensor's range
+    wt = torch.from_numpy(w.reshape(rows, cols, 1, 1).copy())
+    ones = torch.ones(cols); zeros_w = torch.ones(cols)
+    d_ref = O.bias_delta(w.reshape(rows, cols, 1, 1), np.ones(cols, np.float32))
+    sess = Session()
+    li = sess.add_layer(wt, None)
+    ow, ob = sess.bind(zeros_w), sess.bind(ones)
+    sess.upload()
+    doffs = sess.run_bias_correct([dict(layer=li, signed=False, level=0, next_bn_b_off=-1,
+                                        terms=[dict(bn_w_off=ow, bn_b_off=ob, n=cols, relu=False, op="set")])])
+    d_gpu = sess.view(doffs[0], rows).cpu().numpy()
+    step = np.float32(scale)
+    assert np.abs(d_gpu.astype(np.float64) - d_ref.astype(np.float64)).max() < 1e-3 * step, \
+        "a code differs from the reference's (error in quantization steps: %g)" % (np.abs(d_gpu - d_ref).max() / step)
