@@ -228,28 +228,6 @@ __host__ __device__ inline QuantScalars quant_scalars(double mn, double mx, int 
   return q;
 }
 
-// The division of quantize.py:71 when only the rounded CODE matters (bias correction: eps = Q(w) - w).  t * fp32(1/scale)
-// differs from the IEEE quotient t / scale by at most 1.6 * 2^-23 * |quotient| (two roundings of the reciprocal, one of the
-// product) plus the quotient's own half ulp, i.e. by less than max(|qmin|, |qmax|) * 2^-21 after the clamp; rint() of the two
-// can therefore only differ when the product lands within that distance of a half-integer.  `guard` = 0.5 - max|q| * 2^-20
-// (twice the bound): inside the guard the cheap product decides the code, outside the exact division is redone - the result is
-// the reference's code in every case, at ~5 instructions instead of ~10 for all but ~0.05 % of the elements.
-__device__ __forceinline__ float quant_guard(const QuantScalars& q) {
-  return 0.5f - fmaxf(fabsf(q.qmin), fabsf(q.qmax)) * 9.5367431640625e-07f;   // 2^-20
-}
-__device__ __forceinline__ float fake_quant_div_guarded(float x, const QuantScalars& q, float guard) {
-  const float t = __fadd_rn(x, q.neg_min);
-  float a = __fmul_rn(t, q.inv_scale);
-  a = fminf(fmaxf(a, q.qmin), q.qmax);
-  float k = rintf(a);
-  if (!(fabsf(__fsub_rn(a, k)) <= guard)) {
-    float d = __fdiv_rn(t, q.scale);
-    d = fminf(fmaxf(d, q.qmin), q.qmax);
-    k = rintf(d);
-  }
-  return __fadd_rn(__fmul_rn(k, q.scale), q.min_v);
-}
-
 // quantize.py:70-74, one element.  Every op is individually rounded (no FMA contraction).
 template <bool RECIP>
 __device__ __forceinline__ float fake_quant(float x, const QuantScalars& q, float* code = nullptr) {

@@ -295,7 +295,6 @@ template <int TPR, bool RAW>
 __device__ __forceinline__ double bc_row(const float* __restrict__ row, int cols, int kk, const float* __restrict__ ex,
                                          const QuantScalars& q, int lane) {
   double acc = 0.0;
-  const float guard = quant_guard(q);    // see fake_quant_div_guarded: the reference's codes at half the instructions
   for (int j = lane; j < cols; j += TPR) {
     const float* p = row + (size_t)j * kk;
     float E = 0.f;
@@ -303,9 +302,9 @@ __device__ __forceinline__ double bc_row(const float* __restrict__ row, int cols
       for (int k = 0; k < kk; ++k) E = __fadd_rn(E, p[k]);
     } else if (kk == 9) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) { const float w = p[k]; E = __fadd_rn(E, __fsub_rn(fake_quant_div_guarded(w, q, guard), w)); }
+      for (int k = 0; k < 9; ++k) { const float w = p[k]; E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w)); }
     } else {
-      for (int k = 0; k < kk; ++k) { const float w = p[k]; E = __fadd_rn(E, __fsub_rn(fake_quant_div_guarded(w, q, guard), w)); }
+      for (int k = 0; k < kk; ++k) { const float w = p[k]; E = __fadd_rn(E, __fsub_rn(fake_quant<false>(w, q), w)); }
     }
     acc += (double)E * (double)ex[j];
   }

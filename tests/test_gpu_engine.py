@@ -361,9 +361,8 @@ def test_fused_fold_scan_and_range_hints_equal_the_unfused_calls(shapes):
 
 
 def test_bias_correction_codes_at_rounding_boundaries_are_the_references():
-    """The correction's quantizer decides most codes with a reciprocal multiplication and re-does the IEEE division only near
-    half-integers (csrc/common.cuh fake_quant_div_guarded).  Weights placed ON and within a few ulps of every rounding
-    boundary of the 8-bit grid must still give the reference's codes: with E[x] = 1 the row's delta is sum(eps) in fp64, so a
+    """Weights placed ON and within a few ulps of every rounding boundary of the 8-bit grid must give the reference's codes
+    (true IEEE division, clamp, round-half-even - quantize.py:70-74): with E[x] = 1 the row's delta is sum(eps) in fp64, so a
     single wrong code shows as an error of one quantization step."""
     from dfq_b200.engine import Session
     rng = np.random.default_rng(7)
