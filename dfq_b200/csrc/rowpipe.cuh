@@ -78,7 +78,10 @@ constexpr int kPipeStages = DFQ_PIPE_STAGES;   // stages per CTA
 constexpr int kPipeCtas = DFQ_CTAS;             // co-resident CTAs per SM the kernels are compiled for
 constexpr int kStageFloats = 4608;                 // 18 KB: one [512,3,3] row, 8 rows of 576, 512 depthwise rows ...
 constexpr int kStageBytes = kStageFloats * 4;
-constexpr int kPipeMaxRows = 64;                   // rows per tile at most: spreads layers of short rows (depthwise) over the grid
+#ifndef DFQ_PIPE_MAX_ROWS
+#define DFQ_PIPE_MAX_ROWS 32
+#endif
+constexpr int kPipeMaxRows = DFQ_PIPE_MAX_ROWS;                   // rows per tile at most: spreads layers of short rows (depthwise) over the grid
 
 // rows per tile for a matrix of `row_len`-float rows (host and device must agree)
 __host__ __device__ inline int pipe_rows_per_tile(int row_len) {
