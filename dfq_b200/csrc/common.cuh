@@ -147,7 +147,7 @@ __device__ __forceinline__ TileSpan tile_span(const long long* __restrict__ ptr,
 // within G*kTileBlock tiles (TLB reach; measured: the contiguous split loses 30 % at a 39 GB arena), while a CTA still
 // stays on one layer for kTileBlock tiles.
 #ifndef DFQ_TILE_BLOCK
-#define DFQ_TILE_BLOCK 16
+#define DFQ_TILE_BLOCK 64
 #endif
 constexpr long long kTileBlock = DFQ_TILE_BLOCK;
 
