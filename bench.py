@@ -87,9 +87,9 @@ class ClockSampler(threading.Thread):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_cle_engine from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full_1024layers.md: 19.407 GB read + 19.548 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The kernel's traffic is linear
+# (profiles/r1_ncu_full_1024layers.md: 19.375 GB read + 19.434 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The kernel's traffic is linear
 # in the number of pairs (every block is identical), so the figure is scaled to the benched size; None for other sweep counts.
-NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.955e9
+NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.809e9
 NCU_TRAFFIC_SOURCE = "ncu --set full capture at 1024 pairs (profiles/r1_ncu_full_1024layers.md), scaled linearly to the benched pairs"
 
 
