@@ -1,0 +1,100 @@
+"""dfq_b200.trace: the torch.fx graph/bottoms producer against the reference tracer's committed topologies and against
+hand-written expectations."""
+import json
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from dfq_b200 import trace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _shape(graph, bottoms):
+    """Structure only: [(type-or-stem, [indices of bottoms])] in graph order."""
+    idx = {k: i for i, k in enumerate(graph)}
+    out = []
+    for k, v in graph.items():
+        t = type(v).__name__ if isinstance(v, nn.Module) else re.sub(r"_?\d+$", "", v)
+        out.append((t, None if bottoms[k] is None else [idx[b] for b in bottoms[k]]))
+    return out
+
+
+def _gold_shape(name):
+    topo = json.load(open(os.path.join(GOLD, "topology_%s.json" % name)))
+    idx = {n["key"]: i for i, n in enumerate(topo["nodes"])}
+    out = []
+    for n in topo["nodes"]:
+        t = re.sub(r"_?\d+$", "", n["key"]) if n["type"] in ("Func", "Data") else n["type"]
+        t = "add" if t == "iadd" else t     # fx sees `out += identity` as operator.add (Proxy has no __iadd__); the walks test 'add' in key
+        out.append((t, None if n["bottoms"] is None else [idx[b] for b in n["bottoms"]]))
+    return out
+
+
+def test_resnet18_matches_the_reference_tracers_topology():
+    tv = pytest.importorskip("torchvision")
+    model = tv.models.resnet18().eval()
+    graph, bottoms = trace.trace_graph(model)
+    assert _shape(graph, bottoms) == _gold_shape("resnet18")
+    # module nodes are keyed by id(module) and ARE the model's modules: calibrating the graph calibrates the model
+    assert graph[id(model.conv1)] is model.conv1 and graph[id(model.fc)] is model.fc
+
+
+class _Block(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c1 = nn.Conv2d(8, 16, 3, padding=1, bias=False); self.b1 = nn.BatchNorm2d(16)
+        self.c2 = nn.Conv2d(16, 16, 3, padding=1, groups=16, bias=False); self.b2 = nn.BatchNorm2d(16)
+        self.c3 = nn.Conv2d(16, 8, 1, bias=False); self.b3 = nn.BatchNorm2d(8)
+        self.act = nn.ReLU()
+        self.side = nn.Conv2d(8, 8, 1); self.sb = nn.BatchNorm2d(8)
+        self.fc = nn.Linear(16, 5)
+
+    def forward(self, x):
+        y = self.act(self.b1(self.c1(x)))
+        y = F.relu(self.b2(self.c2(y)))                 # functional activation -> module node
+        y = self.b3(self.c3(y))
+        y = x + y                                       # residual
+        z = self.sb(self.side(F.pad(x, (0, 0, 0, 0))))
+        y = torch.cat([y, z], 1)
+        y = y.mean(3).mean(2)
+        return self.fc(y.view(y.size(0), -1))
+
+
+def test_functional_ops_reuse_and_relations():
+    from dfq_b200.utils.relation import create_relation
+    m = _Block().eval()
+    graph, bottoms = trace.trace_graph(m)
+    kinds = [t for t, _ in _shape(graph, bottoms)]
+    assert kinds == ["Data", "Conv2d", "BatchNorm2d", "ReLU", "Conv2d", "BatchNorm2d", "ReLU", "Conv2d", "BatchNorm2d", "add",
+                     "F.pad", "Conv2d", "BatchNorm2d", "torch.cat", "torch.mean", "torch.mean", "view", "Linear"]
+    keys = list(graph)
+    assert bottoms[keys[9]] == ["Data", keys[8]]                        # x + y
+    assert bottoms[keys[13]] == [keys[9], keys[12]]                     # cat([y, z])
+    assert bottoms[keys[11]] == [keys[10]] and bottoms[keys[10]] == ["Data"]
+    # the walks accept it: conv1 -> depthwise -> pointwise is one equalization chain
+    for k in (id(m.b1), id(m.b2), id(m.b3), id(m.sb)):                  # what merge_batchnorm would have registered
+        graph[k].fake_weight = torch.ones(graph[k].num_features); graph[k].fake_bias = torch.zeros(graph[k].num_features)
+    rels = create_relation(graph, bottoms, [nn.Conv2d, nn.Linear])
+    pairs = [(r.get_idxs()[0], r.get_idxs()[1]) for r in rels]
+    assert (id(m.c1), id(m.c2)) in pairs and (id(m.c2), id(m.c3)) in pairs
+
+
+def test_module_called_twice_gets_two_nodes():
+    class Twice(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(4, 4, 1); self.r = nn.ReLU()
+
+        def forward(self, x):
+            return self.r(self.c(self.r(x)))
+    m = Twice()
+    graph, bottoms = trace.trace_graph(m)
+    relu_keys = [k for k, v in graph.items() if v is m.r]
+    assert len(relu_keys) == 2 and relu_keys[0] == id(m.r) and isinstance(relu_keys[1], str)
+    assert bottoms[id(m.c)] == [relu_keys[0]] and bottoms[relu_keys[1]] == [id(m.c)]
