@@ -198,3 +198,36 @@ def test_relations_in_arbitrary_order_use_the_per_relation_path():
         assert np.array_equal(c.weight.detach().numpy(), l.w)
         if l.b is not None:
             assert np.array_equal(c.bias.detach().numpy(), l.b)
+
+
+def test_traced_torchvision_resnet18_calibrates_end_to_end():
+    """No reference tracer in the loop: torch.fx graph (dfq_b200.trace) of a torchvision ResNet-18 -> one-residency
+    calibration; equal to the drop-in calls run one after the other on an identical copy, and the model still runs."""
+    tv = pytest.importorskip("torchvision")
+    import copy
+    from dfq_b200 import dfq
+    from dfq_b200.calibrate import GraphCalibration
+    from dfq_b200.trace import trace_graph
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    torch.manual_seed(0)
+    ma = tv.models.resnet18().eval()
+    for m in ma.modules():                      # non-trivial BN statistics
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    mb = copy.deepcopy(ma)
+    x = torch.randn(2, 3, 64, 64)
+    y0 = ma(x)
+    ga, ba = trace_graph(ma)
+    LT.merge_batchnorm(ma, ga, ba, TARG)
+    rels = create_relation(ga, ba, TARG)
+    dfq.cross_layer_equalization(ga, rels, TARG)
+    dfq.bias_correction(ga, ba, TARG)
+    gb, bb = trace_graph(mb)
+    cal = GraphCalibration(gb, bb, TARG)
+    res = cal.run(equalize=True, correction=False)
+    assert res.n_sweeps == dfq.cross_layer_equalization.last_result.n_sweeps and len(cal.relations) == len(rels) == 8
+    # equalization alone leaves the function unchanged (scaling is absorbed by ReLU's positive homogeneity)
+    assert torch.allclose(mb(x), y0, rtol=1e-3, atol=1e-3)
+    for ra, rb in zip(rels, cal.relations):
+        assert np.array_equal(ra.S.numpy(), rb.S.numpy())
