@@ -328,7 +328,9 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_e2e:
         from dfq_b200.workload import HostStackCalibrator
         chunk_blocks = max(1, args.e2e_chunk // 2)                # 32 layer pairs = 302 MB per chunk
-        n_chunks = max(2, min(args.e2e_layers, layers) // (2 * chunk_blocks))
+        # pinned host memory is a per-box resource: 2 x 4.8 GB per rank at 512 pairs; keep the box total at what 4 ranks use
+        e2e_pairs = args.e2e_layers if world <= 4 else max(2 * chunk_blocks * 2, args.e2e_layers * 4 // world)
+        n_chunks = max(2, min(e2e_pairs, layers) // (2 * chunk_blocks))
         e_layers = n_chunks * 2 * chunk_blocks
         del pristine
         torch.cuda.empty_cache()
