@@ -11,8 +11,8 @@ arithmetic runs in libdfq_sm100.so:
 
 Numerics.  The reference runs the same Python on CPU tensors (weights during
 calibration) and on CUDA tensors (activations, per-forward weights during inference), and PyTorch's two
-backends differ in ONE op: ``div_(python_float)`` is a true division on CPU and a multiply by the fp32
-reciprocal on CUDA.  ``quantize`` follows the device of its input: CPU tensors are staged through the GPU
+backends differ in ONE op: ``div_(python_float)`` is a true division on CPU and, on CUDA, a multiply by
+``fp32(1.0 / scale)`` - the reciprocal formed in DOUBLE from the Python scalar, then rounded (probed on B200).  ``quantize`` follows the device of its input: CPU tensors are staged through the GPU
 and computed with true division (bit-identical to the reference's CPU result), CUDA tensors use the
 reciprocal form (bit-identical to the reference's CUDA result).  There is no CPU implementation.
 """
