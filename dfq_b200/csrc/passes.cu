@@ -6,6 +6,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -578,6 +581,9 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
                                 const DfqBcLayer* bc, int32_t n_bc, const DfqExpectTerm* terms, int32_t n_terms,
                                 const int32_t* level_ptr, int32_t n_levels, int32_t num_bits, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool trace = getenv("DFQ_TRACE") != nullptr;
+  const auto h0 = std::chrono::steady_clock::now();
+  auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); };
   DFQ_REQUIRE(arena && layers && bc && terms && level_ptr, "null argument");
   if (n_bc <= 0 || n_levels <= 0) return 0;
   DFQ_REQUIRE(level_ptr[0] == 0 && level_ptr[n_levels] == n_bc, "levels must partition the layer list");
@@ -619,7 +625,9 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   int32_t* dLP = tp.ptr<int32_t>(iLP); long long* dRP = tp.ptr<long long>(iRP); long long* dMP = tp.ptr<long long>(iMP);
   int32_t* dLL = tp.ptr<int32_t>(iLL);
   void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP, &dMP, &dLL};
+  const double h_prep = ms_since();
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, dyn, st));
   tp.release(st);
+  if (trace) fprintf(stderr, "[dfq_bias_correct] host ms: tables+upload %.3f, launch returned %.3f\n", h_prep, ms_since());
   return 0;
 }
