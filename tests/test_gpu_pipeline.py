@@ -231,3 +231,55 @@ def test_traced_torchvision_resnet18_calibrates_end_to_end():
     assert torch.allclose(mb(x), y0, rtol=1e-3, atol=1e-3)
     for ra, rb in zip(rels, cal.relations):
         assert np.array_equal(ra.S.numpy(), rb.S.numpy())
+
+
+def test_resnet18_activation_ranges_over_64_images():
+    """BASELINE configs[2]: ResNet-18 with QuantN* layers, observers driven in update_stat mode over 64 synthetic images
+    (4 batches of 16, clamp(N(0,1)) like the reference's fallback data).  Every observer's running_min/max must equal the
+    statistic of quantize.py:103-107 (per-sample max -> batch mean -> running max) computed by plain torch on the very tensors
+    the observers saw, and the device-resident path must never have synchronised to do so."""
+    tv = pytest.importorskip("torchvision")
+    from dfq_b200.improve_dfq import set_update_stat
+    from dfq_b200.utils.quantize import QuantMeasure, QuantNConv2d, QuantNLinear
+    torch.manual_seed(0)
+    model = tv.models.resnet18().eval()
+
+    def swap(parent):
+        for name, ch in list(parent.named_children()):
+            if type(ch) is nn.Conv2d:
+                q = QuantNConv2d(ch.in_channels, ch.out_channels, ch.kernel_size, ch.stride, ch.padding, ch.dilation, ch.groups,
+                                 ch.bias is not None)
+                q.weight.data.copy_(ch.weight.data)
+                if ch.bias is not None:
+                    q.bias.data.copy_(ch.bias.data)
+                setattr(parent, name, q)
+            elif type(ch) is nn.Linear:
+                q = QuantNLinear(ch.in_features, ch.out_features, ch.bias is not None)
+                q.weight.data.copy_(ch.weight.data); q.bias.data.copy_(ch.bias.data)
+                setattr(parent, name, q)
+            else:
+                swap(ch)
+    swap(model)
+    model = model.cuda().eval()
+    layers = [m for m in model.modules() if isinstance(m, (QuantNConv2d, QuantNLinear))]
+    assert len(layers) == 21
+    set_update_stat(model, [QuantMeasure], True)
+    ref = {id(l): [torch.zeros((), device="cuda"), torch.zeros((), device="cuda")] for l in layers}
+
+    def pre_hook(mod, args):
+        x = args[0].detach()
+        b = x.size(0)
+        mx = x.reshape(b, -1).max(-1)[0].mean(); mn = x.reshape(b, -1).min(-1)[0].mean()
+        ref[id(mod)][0] = torch.minimum(ref[id(mod)][0], mn); ref[id(mod)][1] = torch.maximum(ref[id(mod)][1], mx)
+    hooks = [l.register_forward_pre_hook(pre_hook) for l in layers]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    with torch.no_grad():
+        for _ in range(4):
+            model(torch.randn(16, 3, 64, 64, device="cuda", generator=g).clamp_(-2.5, 2.5))
+    for h in hooks:
+        h.remove()
+    for l in layers:
+        mn, mx = float(l.quant.running_min), float(l.quant.running_max)
+        rmn, rmx = float(ref[id(l)][0]), float(ref[id(l)][1])
+        assert abs(mn - rmn) <= 1e-6 * max(1.0, abs(rmn)) and abs(mx - rmx) <= 1e-6 * max(1.0, abs(rmx)), (mn, rmn, mx, rmx)
+    assert sum(1 for l in layers if float(l.quant.running_max) > 0) == len(layers)
