@@ -395,3 +395,29 @@ def test_bias_correction_codes_at_rounding_boundaries_are_the_references():
     step = np.float32(scale)
     assert np.abs(d_gpu.astype(np.float64) - d_ref.astype(np.float64)).max() < 1e-3 * step, \
         "a code differs from the reference's (error in quantization steps: %g)" % (np.abs(d_gpu - d_ref).max() / step)
+
+
+def test_invalid_descriptors_are_rejected_with_a_message_not_a_crash():
+    """Error behaviour at the C boundary: inconsistent tables return DFQ_E_ARG and set dfq_last_error (surfaced as DfqError)
+    before anything is launched; the arena is untouched and the session stays usable."""
+    from dfq_b200._lib import DfqError
+    from dfq_b200.engine import Session
+    sess = Session()
+    w1 = torch.randn(8, 4, 3, 3); w2 = torch.randn(6, 8, 3, 3)
+    l1 = sess.add_layer(w1, None); l2 = sess.add_layer(w2, None)
+    sess.upload()
+    plan = sess.plan_cle([(l1, l2, -1, -1)])
+    before = sess.view(0, sess.arena.numel()).clone()
+    bad = dict(plan); bad["rt"] = plan["rt"].copy(); bad["rt"]["channels"] = 7               # != rows(first)
+    with pytest.raises(DfqError, match="channels"):
+        sess.run_cle_plan(bad)
+    bad = dict(plan); bad["lt"] = plan["lt"].copy(); bad["lt"]["w_off"][l2] = sess.arena.numel()   # weight outside the arena
+    with pytest.raises(DfqError, match="arena"):
+        sess.run_cle_plan(bad)
+    bad = dict(plan); bad["step_layers"] = plan["step_layers"].copy(); bad["step_layers"][0] = 99
+    with pytest.raises(DfqError, match="layer index"):
+        sess.run_cle_plan(bad)
+    n = w1.numel() + w2.numel()
+    assert torch.equal(sess.view(0, sess.arena.numel())[:n], before[:n]), "weights touched by a rejected call"
+    res = sess.run_cle_plan(plan)                                                          # still usable
+    assert res.n_sweeps >= 1
