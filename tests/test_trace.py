@@ -98,3 +98,50 @@ def test_module_called_twice_gets_two_nodes():
     relu_keys = [k for k, v in graph.items() if v is m.r]
     assert len(relu_keys) == 2 and relu_keys[0] == id(m.r) and isinstance(relu_keys[1], str)
     assert bottoms[id(m.c)] == [relu_keys[0]] and bottoms[relu_keys[1]] == [id(m.c)]
+
+
+def test_traced_torchvision_mobilenetv2_calibrates_like_the_separate_calls(monkeypatch):
+    """torchvision's MobileNetV2 (functional adaptive_avg_pool2d + flatten, `x + self.conv(x)` residuals, ReLU6) through the
+    fx tracer and the one-residency plan == the drop-in calls one after the other (arithmetic by the oracle-backed fake)."""
+    tv = pytest.importorskip("torchvision")
+    import copy
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fakelib
+    fakelib.install(monkeypatch)
+    from dfq_b200 import dfq
+    from dfq_b200.calibrate import GraphCalibration
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils.relation import create_relation
+    torch.manual_seed(0)
+    ma = tv.models.mobilenet_v2(width_mult=0.25).eval()
+    for m in ma.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+
+    def relu6_to_relu(parent):            # what the reference's --relu flag does (main_cls.py: switch_layers {ReLU6: ReLU});
+        for name, ch in list(parent.named_children()):      # ReLU6 is not positively homogeneous, so create_relation stops at it
+            if isinstance(ch, nn.ReLU6):
+                setattr(parent, name, nn.ReLU())
+            else:
+                relu6_to_relu(ch)
+    ga0, ba0 = trace.trace_graph(ma)
+    assert len(create_relation(ga0, ba0, [nn.Conv2d, nn.Linear])) <= 1          # with ReLU6 in place nothing can be equalized
+    relu6_to_relu(ma)
+    mb = copy.deepcopy(ma)
+    targ = [nn.Conv2d, nn.Linear]
+    ga, ba = trace.trace_graph(ma)
+    kinds = {type(v).__name__ if isinstance(v, nn.Module) else re.sub(r"_?\d+$", "", v) for v in ga.values()}
+    assert {"Conv2d", "BatchNorm2d", "ReLU", "add", "AdaptiveAvgPool2d", "torch.flatten", "Dropout", "Linear"} <= kinds
+    LT.merge_batchnorm(ma, ga, ba, targ)
+    rels = create_relation(ga, ba, targ)
+    assert len(rels) >= 30
+    dfq.cross_layer_equalization(ga, rels, targ, converge_thres=1e-2)
+    dfq.bias_correction(ga, ba, targ)
+    gb, bb = trace.trace_graph(mb)
+    cal = GraphCalibration(gb, bb, targ)
+    res = cal.run(equalize=True, correction=True, converge_thres=1e-2)
+    assert res.n_sweeps == dfq.cross_layer_equalization.last_result.n_sweeps and len(cal.relations) == len(rels)
+    for (na, pa), (nb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert np.array_equal(pa.detach().numpy(), pb.detach().numpy()), na
