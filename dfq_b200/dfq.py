@@ -184,6 +184,7 @@ def bias_absorption(graph, relations, bottoms, N=3):
         return False
 
     with torch.no_grad():
+        todo = []
         for rr in relations:
             first, second, bn_idx = rr.get_idxs()
             if not relu_between(second, first):
@@ -195,16 +196,32 @@ def bias_absorption(graph, relations, bottoms, N=3):
             for key in (first, second):
                 if graph[key].bias is None:
                     _zero_bias(graph[key])
-            # wc = (sum_k W2) @ c per group (dfq.py:139-153): one pass over W2 on the device
+            todo.append((first, second, bn, c))
+        if not todo:
+            return
+        # wc = (sum_k W2) @ c per group (dfq.py:139-153): one pass over every W2, all relations in ONE launch.  The
+        # relations are independent (c reads the FIRST layer's BN, which no relation writes before its own turn) except
+        # for the order of the two updates that land in a middle layer's bias: `+= wc` as second of relation k, then
+        # `-= c` as first of relation k+1 (dfq.py:162-164).  Device first (all the `+= wc`), host afterwards (all the
+        # `-= c`) keeps that order whenever a layer's incoming relation precedes its outgoing one (create_relation's
+        # order); any other list falls back to one launch per relation.
+        seconds = [t[1] for t in todo]
+        batched = len(set(seconds)) == len(seconds) and all(
+            t[0] not in seconds or seconds.index(t[0]) < i for i, t in enumerate(todo))
+        for group in ([todo] if batched else [[t] for t in todo]):
             sess = Session()
-            l2 = sess.add_layer(graph[second].weight, graph[second].bias, weight_writeback=False)
-            oc = sess.bind(c, writeback=False)
+            items = []
+            for first, second, bn, c in group:
+                l2 = sess.add_layer(graph[second].weight, graph[second].bias, weight_writeback=False)
+                oc = sess.bind(c, writeback=False)
+                items.append(dict(layer=l2, signed=False, level=0, next_bn_b_off=-1, raw_sum=True, add=True,
+                                  terms=[dict(bn_w_off=oc, bn_b_off=oc, n=c.numel(), relu=False, op="set")]))
             sess.upload()
-            sess.run_bias_correct([dict(layer=l2, signed=False, level=0, next_bn_b_off=-1, raw_sum=True, add=True,
-                                        terms=[dict(bn_w_off=oc, bn_b_off=oc, n=c.numel(), relu=False, op="set")])])
+            sess.run_bias_correct(items)
             sess.download()
-            graph[first].bias.data.add_(-c.to(graph[first].bias.device))
-            bn.fake_bias.data.add_(-c)
+            for first, second, bn, c in group:
+                graph[first].bias.data.add_(-c.to(graph[first].bias.device))
+                bn.fake_bias.data.add_(-c)
 
 
 def clip_weight(graph, range_clip=[-15, 15], targ_type=[nn.Conv2d, nn.Linear]):

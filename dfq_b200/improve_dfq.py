@@ -5,10 +5,12 @@
                                                    first layer's range to the preprocessing constants
     set_update_stat      improve_dfq.py:299-309   toggle update_stat on every module of the given types
 
+    GradHook, ModuleHook improve_dfq.py:12-100    hook holders; `ZeroQ/distill_data.py:28` imports GradHook by name
+
 The remaining names of improve_dfq.py (update_scale, set_scale, transform_quant_layer, bias_correction_distill) are the
-author's abandoned learned-scale experiment (README.md:194-195); the main scripts import them but never call them on the
-supported flag combinations.  They are forwarded to the reference implementation when it is importable and raise
-otherwise - they are outside the calibration path.
+author's abandoned learned-scale experiment (README.md:194-195); the main scripts import them but every call site is
+commented out.  The names exist (the unmodified scripts import them) and raise NotImplementedError when called - they are
+outside the calibration path.
 """
 import torch
 
@@ -48,24 +50,68 @@ def set_update_stat(model, targ_type, update_stat):
             child.set_update_stat(update_stat)
 
 
-def _forward_to_reference(name):
+class ModuleHook(object):
+    """Forward hook that remembers the module it fired on together with that call's inputs and outputs
+    (improve_dfq.py:82-100; imported by name by the reference's experiments)."""
+
+    def __init__(self):
+        self.module = self.inputs = self.outputs = None
+
+    def hook(self, module, input, output):
+        self.module, self.inputs, self.outputs = module, input, output
+
+    def clear(self):
+        self.module = self.inputs = self.outputs = None
+
+
+class GradHook(object):
+    """Holder of a weight and its optional (prev-)scale vectors with pass-through gradient hooks
+    (improve_dfq.py:12-80).  `ZeroQ/distill_data.py:28` imports the name; every use of it there is commented out and both
+    gradient hooks of the reference return their argument unchanged on their first line - that live behaviour is what is
+    kept; the outlier mask is still computed so `.mask` exists."""
+
+    def __init__(self, weight, scale=None, scale_prev=None, merge_scale=None, merge_scale_prev=None):
+        self.weight, self.scale, self.scale_prev = weight, scale, scale_prev
+        self.merge_scale, self.merge_scale_prev = merge_scale, merge_scale_prev
+        self.update_mask()
+
+    def get_weight_scaled(self):
+        w = self.weight
+        if self.scale_prev is not None:
+            w = self.merge_scale_prev(w, self.scale_prev)
+        if self.scale is not None:
+            w, _ = self.merge_scale(w, None, self.scale)
+        return w
+
+    def update_mask(self):
+        with torch.no_grad():
+            # clone: get_weight_scaled returns the parameter itself when no scale is attached, and the masking is in place
+            w = self.get_weight_scaled().detach().clone()
+            mean, std = w.mean(), torch.sqrt(torch.var(w))
+            # improve_dfq.py:34-35 indexes with an integer tensor (values 1 or 2: inside one or both 2-sigma bounds), i.e.
+            # it zeroes the slices w[1] and w[2] whenever they are addressed - reproduced literally
+            idx = (w < (mean + 2 * std)).long() + (w > (mean - 2 * std)).long()
+            w[idx] = 0
+            self.mask = torch.abs(w) / torch.abs(w).max()
+
+    def hook_mask_grad_tensor(self, grad):
+        return grad
+
+    def hook_mask_grad_input(self, m, grad_input, grad_output):
+        return grad_input
+
+
+def _not_on_the_path(name):
     def call(*args, **kwargs):
-        import importlib.util
-        import os
-        root = os.environ.get("DFQ_REFERENCE_ROOT", "/root/reference")
-        path = os.path.join(root, "improve_dfq.py")
-        if not os.path.isfile(path):
-            raise NotImplementedError("%s belongs to the reference's abandoned learned-scale experiment and is not part "
-                                      "of the calibration path; reference tree not found at %s" % (name, root))
-        spec = importlib.util.spec_from_file_location("_ref_improve_dfq", path)
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        return getattr(mod, name)(*args, **kwargs)
+        raise NotImplementedError(
+            "%s is part of the reference's abandoned learned-scale experiment (README.md:194-195, every call site in "
+            "main_cls/main_seg/main_ssd is commented out) and is outside the calibration path dfq_b200 implements "
+            "(SURVEY.md section 2, row 6); the name exists so that the unmodified main scripts import." % name)
     call.__name__ = name
     return call
 
 
-update_scale = _forward_to_reference("update_scale")
-set_scale = _forward_to_reference("set_scale")
-transform_quant_layer = _forward_to_reference("transform_quant_layer")
-bias_correction_distill = _forward_to_reference("bias_correction_distill")
+update_scale = _not_on_the_path("update_scale")
+set_scale = _not_on_the_path("set_scale")
+transform_quant_layer = _not_on_the_path("transform_quant_layer")
+bias_correction_distill = _not_on_the_path("bias_correction_distill")

@@ -104,7 +104,7 @@ def tensor_minmax(x):
     """Device tensor [2] = (min(x), max(x)); stays on the GPU."""
     lib = _lib.load()
     xd, _ = _dev_f32(x.detach())
-    out = torch.empty(2, dtype=torch.float32, device=xd.device)
+    out = xd.new_empty((2,))
     _lib.check(lib.dfq_minmax(_ptr(xd), xd.numel(), _ptr(out), _lib.stream_ptr()), "dfq_minmax")
     return out
 
@@ -117,8 +117,8 @@ def per_sample_minmax_mean(x, batch=None):
     if batch is None:
         batch = xd.shape[0]
     per = xd.numel() // batch
-    out = torch.empty(2, dtype=torch.float32, device=xd.device)
-    scratch = torch.empty(2 * batch, dtype=torch.float32, device=xd.device)
+    out = xd.new_empty((2,))
+    scratch = xd.new_empty((2 * batch,))
     _lib.check(lib.dfq_act_minmax_per_sample(_ptr(xd), batch, per, _ptr(out), _ptr(scratch), _lib.stream_ptr()),
                "dfq_act_minmax_per_sample")
     return out
@@ -140,8 +140,8 @@ class UniformQuantize(InplaceFunction):
         if min_value is None or max_value is None:
             # quantize.py:24-35: y = input.view(B // num_chunks, -1); min = y.min(-1)[0].mean(-1)  (0-d tensors)
             stat = per_sample_minmax_mean(input, batch=max(1, input.shape[0] // num_chunks))
-            mn_t = stat[0:1] if min_value is None else torch.full((1,), float(min_value), device=stat.device)
-            mx_t = stat[1:2] if max_value is None else torch.full((1,), float(max_value), device=stat.device)
+            mn_t = stat[0:1] if min_value is None else stat.new_full((1,), float(min_value))
+            mx_t = stat[1:2] if max_value is None else stat.new_full((1,), float(max_value))
             prologue = 2 if input.is_cuda else 1
             res = fake_quant_device_range(input, num_bits, mn_t, mx_t, symmetric, prologue=prologue, out=out)
         else:
@@ -196,8 +196,11 @@ class QuantMeasure(nn.Module):
         lib = _lib.load()
         _lib.require_cuda()
         if not input.is_cuda:
-            # the reference's observers run wherever the model is; this package computes on the GPU
-            return self.forward(input.cuda()).to(input.device)
+            # the reference's observers run wherever the model is (the tracer's forward inside switch_layers feeds CPU
+            # tensors, main_cls.py:77,129); this package computes on the GPU and hands the result back where it came from
+            staged, from_cpu = _dev_f32(input)
+            if from_cpu and staged.device != input.device:
+                return self.forward(staged).to(input.device)
         self._buffers_on(input.device)
         stat = None
         if self.update_stat:

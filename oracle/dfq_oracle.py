@@ -102,15 +102,17 @@ def quantize_error(w: np.ndarray, num_bits: int = 8, signed: bool = False) -> np
 # --------------------------------------------------------------------------------------------
 # BN fold: utils/layer_transform.py:246-272
 # --------------------------------------------------------------------------------------------
-def bn_fold(w: np.ndarray, b: Optional[np.ndarray], gamma, beta, mean, var, eps: float):
-    """Returns (W', b', fake_weight, fake_bias).  Op order follows layer_transform.py:251,260-261."""
+def bn_fold(w: np.ndarray, b: Optional[np.ndarray], gamma, beta, mean, var, eps: float, sqrt_fn=None):
+    """Returns (W', b', fake_weight, fake_bias).  Op order follows layer_transform.py:251,260-261.
+    `sqrt_fn`: None = correctly rounded IEEE root (numpy; what the GPU computes); tests that compare with numbers a
+    particular HOST produced with the reference inject that host's torch.sqrt (MKL VML: faithful, not correctly rounded)."""
     w = np.ascontiguousarray(w, dtype=f32)
     O = w.shape[0]
     gamma = np.asarray(gamma, f32); beta = np.asarray(beta, f32)
     mean = np.asarray(mean, f32); var = np.asarray(var, f32)
     if b is None:
         b = np.zeros(O, f32)
-    den = np.sqrt(var + f32(eps))
+    den = (np.sqrt if sqrt_fn is None else sqrt_fn)(var + f32(eps)).astype(f32)
     f = gamma / den                                   # [O]   (:251 quotient formed first)
     w2 = w * f.reshape((O,) + (1,) * (w.ndim - 1))
     b2 = b * f + (beta - (gamma * mean) / den)         # (:260-261 grouping)

@@ -160,7 +160,7 @@ class FakeLib:
             w = self._wview(arena, l)
             b = arena[int(l["bias_off"]): int(l["bias_off"]) + rows]
             w2, b2, fw, fb = O.bn_fold(w.copy(), b.copy(), v(f["gamma_off"]), v(f["beta_off"]), v(f["mean_off"]),
-                                       v(f["var_off"]), float(f["bn_eps"]))
+                                       v(f["var_off"]), float(f["bn_eps"]), sqrt_fn=self.sqrt_fn)
             w[...] = w2; b[...] = b2
             v(f["fake_w_off"])[...] = fw; v(f["fake_b_off"])[...] = fb
             if int(f["scan_go"]) > 0:     # column extrema of the folded weights -> buffer 0

@@ -307,3 +307,13 @@ def test_live_ncnn_table_through_the_product_host_path(monkeypatch):
     assert got_w.shape == gold_w.shape and got_a.shape == gold_a.shape
     assert np.abs(got_w / gold_w - 1).max() < 2e-6, np.abs(got_w / gold_w - 1).max()
     assert np.abs(got_a / gold_a - 1).max() < 5e-6, np.abs(got_a / gold_a - 1).max()
+
+
+@pytest.mark.parametrize("name", ["resnet18", "mobilenetv2"])
+def test_bias_correction_alone_against_reference_produced_numbers_cpu(name, monkeypatch):
+    """CPU twin of tests/test_gpu_entrypoints.py::test_bias_correction_alone_against_reference_produced_numbers: the
+    product's recipe/levels/write-back with the oracle-backed executor vs what the reference's bias_correction produced."""
+    import test_gpu_entrypoints as T
+    fakelib.install(monkeypatch)
+    worst = T.run_bias_correction_against_reference_fixture(name)
+    assert worst < 1e-5

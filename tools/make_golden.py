@@ -12,7 +12,11 @@ build container.  Committed next to its outputs so every fixture can be regenera
   ref_ops.npz             op-level vectors: _layer_equalization on the shapes of Appendix B, UniformQuantize codes,
                           QuantMeasure updates, _quantize_error
 
-usage: python tools/make_golden.py [topology] [mobilenetv2] [resnet18] [deeplab] [ssd] [ops]
+  ref_bc_<model>.npz      the reference's dfq.bias_correction ALONE on seed-regenerable inputs (tests/bc_fixture.py):
+                          every post-correction bias and fake_bias vector + sha256 of every input tensor
+  main_<cls|seg|ssd>.npz  made by tests/main_harness.py --impl reference (the unmodified main scripts end to end)
+
+usage: python tools/make_golden.py [topology] [mobilenetv2] [resnet18] [deeplab] [ssd] [ops] [bc] [minmax]
 """
 import hashlib
 import json
@@ -271,3 +275,27 @@ def quant_minmax_fixture(name="mobilenetv2", seed=0):
 if __name__ == "__main__" and "minmax" in sys.argv[1:]:
     quant_minmax_fixture("mobilenetv2", 0)
     quant_minmax_fixture("resnet18", 3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def bias_correction_fixture(name):
+    """dfq.py:173-293 alone: inputs from tests/bc_fixture.py, outputs of the reference."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bc_fixture
+    graph, bottoms = bc_fixture.build(name)
+    out = {"digests": bc_fixture.input_digests(graph), "seed": np.array(bc_fixture.SEEDS[name])}
+    ref.dfq.bias_correction(graph, bottoms, bc_fixture.TARG)
+    n = 0
+    for i, k in enumerate(graph):
+        m = graph[k]
+        if type(m) in bc_fixture.TARG and m.bias is not None:
+            out["out_b_%d" % i] = m.bias.detach().numpy().copy(); n += 1
+        elif hasattr(m, "fake_bias") and not isinstance(m, str):
+            out["out_fb_%d" % i] = m.fake_bias.numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "ref_bc_%s.npz" % name), **out)
+    print("bc", name, n, "corrected layers")
+
+
+if __name__ == "__main__" and "bc" in sys.argv[1:]:
+    bias_correction_fixture("resnet18")
+    bias_correction_fixture("mobilenetv2")

@@ -8,6 +8,10 @@
 B200 implementation while models, datasets, the tracer (PyTransformer) and the evaluation code stay the reference's.
 Needs the reference checkout (DFQ_REFERENCE_ROOT, default /root/reference), a CUDA device and - for the evaluation the
 scripts run at the end - the datasets at the paths hard-coded in those scripts.
+
+`tests/test_run_main.py` drives exactly this entry (through `tests/main_harness.py`, which adds synthetic datasets and the
+oracle-backed executor on a GPU-less machine) and compares the calibrated model and its outputs with fixtures produced by
+the same unmodified scripts running on the reference's own modules.
 """
 import collections
 import collections.abc
@@ -20,16 +24,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = os.environ.get("DFQ_REFERENCE_ROOT", "/root/reference")
 
+# optional third-party modules the reference imports for visualisation / model zoos / image IO; none is on the path
+_OPTIONAL = ("pydot", "graphviz", "tensorboardX", "matplotlib", "matplotlib.pyplot", "pytorchcv", "pytorchcv.models",
+             "pytorchcv.models.common", "pytorchcv.models.shufflenetv2", "pytorchcv.model_provider", "cv2")
 
-def main():
-    if len(sys.argv) < 2 or sys.argv[1] not in ("cls", "seg", "ssd"):
-        sys.exit("usage: run_main.py cls|seg|ssd [flags of the reference script]")
-    script = os.path.join(REF, "main_%s.py" % sys.argv[1])
-    if not os.path.isfile(script):
-        sys.exit("reference script not found: %s" % script)
+
+def prepare_environment(use_dropin=True):
+    """The shims SURVEY.md section 8(b) lists for torch 2.x / python 3.12, then sys.path: dropin/ (optional), repo, reference."""
     import torch  # noqa: F401  (before the stubs: torch.fx probes pydot)
-    for name in ("pydot", "graphviz", "tensorboardX", "matplotlib", "matplotlib.pyplot", "pytorchcv", "pytorchcv.models",
-                 "pytorchcv.models.common", "pytorchcv.models.shufflenetv2", "pytorchcv.model_provider"):
+    for name in _OPTIONAL:
         try:
             __import__(name)
         except Exception:
@@ -44,18 +47,33 @@ def main():
                 setattr(sys.modules[mod], n, object)
     collections.Mapping = collections.abc.Mapping            # PyTransformer/transformers/utils.py:491
     import torch.optim.lr_scheduler as sched                 # ZeroQ/distill_data.py:160-163 passes verbose=
-    _orig = sched.ReduceLROnPlateau
+    if not getattr(sched.ReduceLROnPlateau, "_dfq_shim", False):
+        _orig = sched.ReduceLROnPlateau
 
-    class _Plateau(_orig):
-        def __init__(self, *a, verbose=None, **kw):
-            super().__init__(*a, **kw)
-    sched.ReduceLROnPlateau = _Plateau
-    torch.optim.lr_scheduler.ReduceLROnPlateau = _Plateau
+        class _Plateau(_orig):
+            _dfq_shim = True
+
+            def __init__(self, *a, verbose=None, **kw):
+                super().__init__(*a, **kw)
+        sched.ReduceLROnPlateau = _Plateau
     sys.dont_write_bytecode = True
-    sys.path[:0] = [os.path.join(ROOT, "dropin"), ROOT, REF]
+    sys.path[:0] = ([os.path.join(ROOT, "dropin")] if use_dropin else []) + [ROOT, REF]
     os.chdir(REF)                                             # relative checkpoint paths in the scripts
-    sys.argv = [script] + sys.argv[2:]
-    runpy.run_path(script, run_name="__main__")
+
+
+def run(which, flags, use_dropin=True):
+    script = os.path.join(REF, "main_%s.py" % which)
+    if not os.path.isfile(script):
+        sys.exit("reference script not found: %s" % script)
+    prepare_environment(use_dropin)
+    sys.argv = [script] + list(flags)
+    return runpy.run_path(script, run_name="__main__")
+
+
+def main():
+    if len(sys.argv) < 2 or sys.argv[1] not in ("cls", "seg", "ssd"):
+        sys.exit("usage: run_main.py cls|seg|ssd [flags of the reference script]")
+    run(sys.argv[1], sys.argv[2:])
 
 
 if __name__ == "__main__":
