@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("DFQ_LIB_OUT") or os.path.join(HERE, "libdfq_sm100.so")
 SOURCES = ["tensor_ops.cu", "cle_engine.cu", "passes.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dfq_b200.h")]
+HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "rowpipe.cuh", "colscan.cuh", "bc_stream.cuh")] + \
+    [os.path.join(HERE, "..", "include", "dfq_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -106,6 +106,7 @@ SIGNATURES = {
     "dfq_range_cols": [_PF, _I64, _I64, _I64, _I64, _PF, _PF, _ST],
     "dfq_mean_abs_diff": [_PF, _PF, _I64, C.c_void_p, _ST],
     "dfq_quant_error": [_PF, _PF, _I64, _PF, C.c_int, C.c_int, _ST],
+    "dfq_selftest_bc_arithmetic": [_PF, _PF, _PF, _I64, _PF, C.c_int, C.c_int, C.c_void_p, _ST],
     "dfq_clamp": [_PF, _I64, C.c_float, C.c_float, _ST],
 }
 

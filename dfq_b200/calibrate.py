@@ -52,9 +52,15 @@ class GraphCalibration:
                         if type(graph[src]) in self.targ_type:
                             bn = graph[key]
                             n = bn.num_features
+                            # fake_weight / fake_bias: output-only mirrors of buffers registered on the BN right here, so
+                            # that they come back inside the ONE device-to-host copy of download()
+                            if not hasattr(bn, "fake_weight"):
+                                bn.register_buffer("fake_weight", torch.zeros(n, device=bn.weight.device))
+                                bn.register_buffer("fake_bias", torch.zeros(n, device=bn.weight.device))
                             v = dict(gamma=sess.bind(bn.weight.detach(), False), beta=sess.bind(bn.bias.detach(), False),
                                      mean=sess.bind(bn.running_mean, False), var=sess.bind(bn.running_var, False),
-                                     fake_w=sess.alloc(n), fake_b=sess.alloc(n), n=n)
+                                     fake_w=sess.bind(bn.fake_weight, True, upload=False),
+                                     fake_b=sess.bind(bn.fake_bias, True, upload=False), n=n, folded=True)
                             self._bn[key] = v
                             self.fold_pairs.append((key, src))
                             folds.append(dict(layer=self._layer[src], bn_eps=bn.eps, gamma_off=v["gamma"], beta_off=v["beta"],
@@ -66,12 +72,6 @@ class GraphCalibration:
                     if type(bn) == bn_type and hasattr(bn, "fake_weight"):
                         self._bn[key] = dict(fake_w=sess.bind(bn.fake_weight), fake_b=sess.bind(bn.fake_bias), n=bn.fake_bias.numel())
             self._fold_plan = sess.plan_bn_fold(folds) if folds else None
-            # fake_weight / fake_bias must exist as attributes for the graph walks below (values arrive at download)
-            for key, v in self._bn.items():
-                bn = graph[key]
-                if not hasattr(bn, "fake_weight"):
-                    bn.register_buffer("fake_weight", torch.zeros(v["n"], device=bn.weight.device))
-                    bn.register_buffer("fake_bias", torch.zeros(v["n"], device=bn.weight.device))
             # ---- equalization plan ---------------------------------------------------------------------------------
             self.relations = create_relation(graph, bottoms, self.targ_type, delete_single=delete_single)
             table = []
@@ -80,6 +80,15 @@ class GraphCalibration:
                 v = self._bn[bn_key]
                 table.append((self._layer[a], self._layer[b], v["fake_w"], v["fake_b"]))
             self._cle_plan = sess.plan_cle(table) if table else None
+            # Relation.S comes back the same way: the accumulated scale vectors are mirrored into host tensors
+            self._S_host = []
+            if self._cle_plan is not None:
+                for off, t in zip(self._cle_plan["s_offs"], table):
+                    n = sess.layer(t[0])["rows"]
+                    first = self.relations[len(self._S_host)].get_idxs()[0]
+                    h = torch.zeros(n, dtype=torch.float32, device=graph[first].weight.device)
+                    sess.mirror(off, h)
+                    self._S_host.append(h)
             # the fold that precedes an equalization also fills the column extrema the equalization starts from
             self._fold_plan_scan = sess.plan_bn_fold(folds, cle_plan=self._cle_plan) if (folds and self._cle_plan) else None
             # ---- bias correction plan ----------------------------------------------------------------------------------
@@ -134,24 +143,17 @@ class GraphCalibration:
     def download(self):
         sess = self.sess
         with torch.no_grad():
-            fakes = {k: (sess.view(v["fake_w"], v["n"]).clone(), sess.view(v["fake_b"], v["n"]).clone())
-                     for k, v in self._bn.items() if "gamma" in v}
-            S = []
-            if self._cle_plan is not None and self.last_cle is not None:
-                for off, t in zip(self._cle_plan["s_offs"], self._cle_plan["relations"]):
-                    S.append(sess.view(off, sess.layer(t[0])["rows"]).clone())
-            sess.download()
+            sess.download()          # weights, biases, fake_weight / fake_bias and the scale vectors: one D2H copy
             eps = _identity_bn_eps()
-            for key, (fw, fb) in fakes.items():
-                bn = self.graph[key]
-                bn.fake_weight = fw.to(bn.weight.device)
-                bn.fake_bias = fb.to(bn.weight.device)
-                bn.weight.fill_(1); bn.running_var.fill_(1); bn.bias.fill_(0); bn.running_mean.fill_(0)
-                bn.eps = eps
-            for rr, s in zip(self.relations, S):
-                first = rr.get_idxs()[0]
-                rr.S = None
-                rr.set_scale_vec(s if self.graph[first].weight.is_cuda else s.cpu())
+            for key, v in self._bn.items():
+                if v.get("folded"):
+                    bn = self.graph[key]
+                    bn.weight.fill_(1); bn.running_var.fill_(1); bn.bias.fill_(0); bn.running_mean.fill_(0)
+                    bn.eps = eps
+            if self._cle_plan is not None and self.last_cle is not None:
+                for rr, s in zip(self.relations, self._S_host):
+                    rr.S = None
+                    rr.set_scale_vec(s.clone())
 
     def run(self, **kw):
         """upload -> fold/equalize/correct/quantize on the device -> download (results in place in the modules)."""

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "rowpipe.cuh"
 #include "colscan.cuh"
+#include "bc_stream.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -499,6 +500,197 @@ k_bc_engine(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bias correction, streaming variant (bc_stream.cuh): warp-autonomous consumers, no CTA barrier per tile
+// ------------------------------------------------------------------------------------------------
+static_assert(kPipeMaxRows <= 32, "a consumer warp retires one row per lane");
+
+// Producer side of one ring phase: this CTA's tiles of tasks [q_begin, q_end) in block-cyclic order, then SKIP items up to
+// a multiple of kBcConsumers, then one END per consumer.  Called by lane 0 of the producer warp only.
+__device__ __forceinline__ void bc_feed(BcRing& ring, unsigned long long& n, const long long* ptr, int q_begin, int q_end,
+                                        const BcGeo& geo) {
+  TileDesc d;
+  MatIter<BcGeo> it;
+  it.start(ptr, q_begin, q_end, geo);
+  while (it.valid()) { it.fill(d); bc_produce(ring, n++, d); it.next(); }
+  d.gptr = nullptr; d.task = -1; d.row0 = d.nrows = d.floats = 0;
+  d.kind = TK_SKIP;
+  while (n % kBcConsumers) bc_produce(ring, n++, d);
+  d.kind = TK_END;
+  for (int i = 0; i < kBcConsumers; ++i) bc_produce(ring, n++, d);
+}
+
+// Consumer side: wait for item n; returns its stage.
+__device__ __forceinline__ int bc_take(BcRing& ring, unsigned long long n) {
+  const int s = (int)(n % kBcStages);
+  mbar_wait(ring.full + s, (uint32_t)((n / kBcStages) & 1));
+  return s;
+}
+__device__ __forceinline__ void bc_give_back(BcRing& ring, int s, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(ring.empty + s);
+}
+
+__global__ void __launch_bounds__(kBcThreads, 1)
+k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __restrict__ B, int nB,
+            const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits,
+            const long long* __restrict__ row_ptr, const long long* __restrict__ mm_ptr) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  BcRing ring;
+  ring.init(ring_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer = (warp == kBcConsumers);
+  unsigned long long n = producer ? 0 : (unsigned long long)warp;     // producer: next sequence number; consumer: my next item
+  const BcGeo geo{arena, L, B};
+
+  // ---- per-tensor min/max of every corrected weight (dfq.py:14 via :218) --------------------------------------
+  for (int i = blockIdx.x * kBcThreads + threadIdx.x; i < nB; i += gridDim.x * kBcThreads) {
+    __stcg(arena + B[i].minmax_off, DFQ_INF);
+    __stcg(arena + B[i].minmax_off + 1, -DFQ_INF);
+  }
+  grid.sync();
+  // caller-vouched column extrema (DfqBcLayer.n_col > 0): a warp per layer reduces them
+  for (int bi = blockIdx.x * (kBcThreads / 32) + warp; bi < nB; bi += gridDim.x * (kBcThreads / 32)) {
+    const DfqBcLayer b = B[bi];
+    if (b.n_col <= 0) continue;
+    float mn = DFQ_INF, mx = -DFQ_INF;
+    for (int j = lane; j < b.n_col; j += 32) {
+      mn = fminf(mn, __ldcg(arena + b.colmin_off + j)); mx = fmaxf(mx, __ldcg(arena + b.colmax_off + j));
+    }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0) { atomic_min_f(arena + b.minmax_off, mn); atomic_max_f(arena + b.minmax_off + 1, mx); }
+  }
+  if (mm_ptr[nB] > 0) {          // the others: streamed through the ring, one min/max pair per tile
+    if (producer) {
+      if (lane == 0) bc_feed(ring, n, mm_ptr, 0, nB, geo);
+    } else {
+      for (;; n += kBcConsumers) {
+        const int s = bc_take(ring, n);
+        const TileDesc d = ring.desc[s];
+        if (d.kind == TK_END) { bc_give_back(ring, s, lane); n += kBcConsumers; break; }
+        if (d.kind != TK_SKIP) {
+          float mn = DFQ_INF, mx = -DFQ_INF;
+          if (d.kind == TK_BULK && (d.floats & 3) == 0) {
+            const float4* b4 = (const float4*)ring.stage(s);
+            for (int i = lane; i < (d.floats >> 2); i += 32) {
+              const float4 v = b4[i];
+              mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+              mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            }
+          } else if (d.kind == TK_BULK) {
+            for (int i = lane; i < d.floats; i += 32) { const float v = ring.stage(s)[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+          } else {
+            for (int i = lane; i < d.floats; i += 32) { const float v = ldg_stream1(d.gptr + i); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+          }
+          mn = warp_min(mn); mx = warp_max(mx);
+          if (lane == 0) { atomic_min_f(arena + B[d.task].minmax_off, mn); atomic_max_f(arena + B[d.task].minmax_off + 1, mx); }
+        }
+        bc_give_back(ring, s, lane);
+      }
+    }
+  }
+  grid.sync();
+
+  for (int lev = 0; lev < n_levels; ++lev) {
+    // ---- E[x] of every layer of this level (dfq.py:228-278); one CTA per layer, terms in order ----
+    for (int bi = level_ptr[lev] + blockIdx.x; bi < level_ptr[lev + 1]; bi += gridDim.x) {
+      const DfqBcLayer b = B[bi];
+      float* ex = arena + b.expect_off;
+      for (int ti = b.term_begin; ti < b.term_end; ++ti) {
+        const DfqExpectTerm t = T[ti];
+        for (int ch = threadIdx.x; ch < t.n; ch += kBcThreads) {
+          const float fb = __ldcg(arena + t.bn_b_off + ch);
+          const float v = t.relu ? relu_gauss_mean(__ldcg(arena + t.bn_w_off + ch), fb) : fb;
+          float* d = ex + t.dst_off + ch;
+          __stcg(d, t.accumulate ? __fadd_rn(__ldcg(d), v) : v);
+        }
+        __syncthreads();
+      }
+    }
+    grid.sync();
+    // ---- eps . E[x] per output row (dfq.py:216-219,281-293) ---------------------------------------------------
+    if (producer) {
+      if (lane == 0) bc_feed(ring, n, row_ptr, level_ptr[lev], level_ptr[lev + 1], geo);
+    } else {
+      int cur = -1, cur_group = -1, so = 1;
+      DfqBcLayer b; DfqLayer l; BcFastQuant f;
+      bool raw = false, exreg = false;
+      float exr[kBcExRegs];
+#pragma unroll
+      for (int c = 0; c < kBcExRegs; ++c) exr[c] = 0.f;
+      for (;; n += kBcConsumers) {
+        const int s = bc_take(ring, n);
+        const TileDesc d = ring.desc[s];
+        if (d.kind == TK_END) { bc_give_back(ring, s, lane); n += kBcConsumers; break; }
+        if (d.kind == TK_SKIP) { bc_give_back(ring, s, lane); continue; }
+        if (d.task != cur) {
+          cur = d.task; cur_group = -1;
+          b = B[cur]; l = L[b.layer];
+          f = bc_fast_quant(quant_scalars((double)__ldcg(arena + b.minmax_off), (double)__ldcg(arena + b.minmax_off + 1),
+                                          num_bits, b.signed_mode), num_bits);
+          so = l.rows / (b.expect_len / l.cols);
+          raw = (b.flags & 1) != 0;
+          exreg = l.cols <= 32 * kBcExRegs;
+        }
+        const int row_len = l.cols * l.kk;
+        if (d.kind == TK_PLAIN) {       // a tile the TMA unit cannot move: the warp fetches it itself
+          for (int i = lane; i < d.floats; i += 32) ring.stage(s)[i] = ldg_stream1(d.gptr + i);
+          __syncwarp();
+        }
+        const float* base = (d.kind == TK_DIRECT) ? d.gptr : ring.stage(s);
+        // lane r requests row r's read-modify-write operands before the tile and retires them after it
+        float old_bias = 0.f, old_next = 0.f, dl = 0.f;
+        if (lane < d.nrows) {
+          old_bias = __ldcg(arena + l.bias_off + d.row0 + lane);
+          if (b.next_bn_b_off >= 0) old_next = __ldcg(arena + b.next_bn_b_off + d.row0 + lane);
+        }
+        for (int r = 0; r < d.nrows; ++r) {
+          const int g = (d.row0 + r) / so;
+          const float* ex = arena + b.expect_off + (size_t)g * l.cols;
+          if (exreg && g != cur_group) {
+            cur_group = g;
+#pragma unroll
+            for (int c = 0; c < kBcExRegs; ++c) { const int j = lane + 32 * c; exr[c] = j < l.cols ? __ldcg(ex + j) : 0.f; }
+          }
+          const float* row = base + (size_t)r * row_len;
+          double acc;
+          if (raw)            acc = exreg ? bc_stream_row<false, true, true>(row, l.cols, l.kk, ex, exr, f, lane)
+                                          : bc_stream_row<false, true, false>(row, l.cols, l.kk, ex, exr, f, lane);
+          else if (f.ok)      acc = exreg ? bc_stream_row<true, false, true>(row, l.cols, l.kk, ex, exr, f, lane)
+                                          : bc_stream_row<true, false, false>(row, l.cols, l.kk, ex, exr, f, lane);
+          else                acc = exreg ? bc_stream_row<false, false, true>(row, l.cols, l.kk, ex, exr, f, lane)
+                                          : bc_stream_row<false, false, false>(row, l.cols, l.kk, ex, exr, f, lane);
+          if (lane == r) dl = (float)acc;
+        }
+        if (lane < d.nrows) {
+          const int ol = d.row0 + lane;
+          __stcg(arena + b.delta_off + ol, dl);
+          __stcg(arena + l.bias_off + ol, __fadd_rn(old_bias, (b.flags & 2) ? dl : -dl));              // dfq.py:292 / :164
+          if (b.next_bn_b_off >= 0) __stcg(arena + b.next_bn_b_off + ol, __fadd_rn(old_next, -dl));   // dfq.py:204-206,293
+        }
+        bc_give_back(ring, s, lane);
+      }
+    }
+    grid.sync();
+  }
+}
+
+// Library self-test hook: the element-wise quantization error Q(w) - w of one tensor computed with the streaming kernel's
+// XU-free arithmetic (eps_fast) and with the plain IEEE chain of quantize.py:70-74 (eps_div); *ok = the per-tensor guard.
+__global__ void k_bc_selftest(const float* __restrict__ w, float* eps_fast, float* eps_div, int64_t n,
+                              const float* __restrict__ minmax2, int num_bits, int symmetric, int* ok) {
+  const QuantScalars q = quant_scalars((double)minmax2[0], (double)minmax2[1], num_bits, symmetric);
+  const BcFastQuant f = bc_fast_quant(q, num_bits);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ok = f.ok;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    eps_fast[i] = bc_qerr<true>(x, f);
+    eps_div[i] = __fsub_rn(fake_quant<false>(x, q), x);
+  }
+}
+
 }  // namespace dfq
 
 using namespace dfq;
@@ -613,6 +805,30 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
     level_local[lv] = ok ? 1 : 0;
   }
   int grid, rc;
+  // Large phases (bandwidth-bound: many tiles per CTA and level) take the streaming kernel, small models (latency-bound:
+  // a few tiles per level, level_local shortcuts) the per-CTA engine.  DFQ_BC_STREAM=0/1 forces one of them.
+  const int sms = std::max(1, sm_count());
+  bool stream_variant = row_ptr[n_bc] >= (long long)16 * sms * n_levels;
+  if (const char* e = getenv("DFQ_BC_STREAM")) stream_variant = atoi(e) != 0;
+  if (stream_variant) {
+    const size_t dyn_s = BcRing::smem_bytes();
+    DFQ_CUDA(cudaFuncSetAttribute(k_bc_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_s));
+    int per_sm = 0;
+    DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bc_stream, kBcThreads, dyn_s));
+    if (per_sm < 1) { set_error("k_bc_stream does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * per_sm, max_tiles));
+    TablePack tp;
+    const int iL = tp.add(layers, n_layers), iB = tp.add(bc, n_bc), iT = tp.add(terms, n_terms);
+    const int iLP = tp.add(level_ptr, n_levels + 1), iRP = tp.add(row_ptr.data(), n_bc + 1), iMP = tp.add(mm_ptr.data(), n_bc + 1);
+    if ((rc = tp.upload(st))) return rc;
+    DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqBcLayer* dB = tp.ptr<DfqBcLayer>(iB); DfqExpectTerm* dT = tp.ptr<DfqExpectTerm>(iT);
+    int32_t* dLP = tp.ptr<int32_t>(iLP); long long* dRP = tp.ptr<long long>(iRP); long long* dMP = tp.ptr<long long>(iMP);
+    void* args[] = {&arena, &dL, &dB, (void*)&n_bc, &dT, &dLP, (void*)&n_levels, (void*)&num_bits, &dRP, &dMP};
+    DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_stream, dim3(grid), dim3(kBcThreads), args, dyn_s, st));
+    tp.release(st);
+    if (trace) fprintf(stderr, "[dfq_bias_correct] streaming variant, grid %d, host ms %.3f\n", grid, ms_since());
+    return 0;
+  }
   const size_t dyn = RowPipe::smem_bytes();
   DFQ_CUDA(cudaFuncSetAttribute(k_bc_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if ((rc = pick_grid((const void*)k_bc_engine, max_tiles, &grid, dyn))) return rc;
@@ -629,5 +845,14 @@ extern "C" int dfq_bias_correct(float* arena, int64_t arena_floats, const DfqLay
   DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_bc_engine, dim3(grid), dim3(kThreads), args, dyn, st));
   tp.release(st);
   if (trace) fprintf(stderr, "[dfq_bias_correct] host ms: tables+upload %.3f, launch returned %.3f\n", h_prep, ms_since());
+  return 0;
+}
+
+extern "C" int dfq_selftest_bc_arithmetic(const float* w, float* eps_fast, float* eps_div, int64_t n, const float* minmax2,
+                                          int num_bits, int symmetric, int* ok_dev, void* stream) {
+  DFQ_REQUIRE(w && eps_fast && eps_div && minmax2 && ok_dev && n > 0, "bad argument");
+  k_bc_selftest<<<(int)std::min<int64_t>(148 * 8, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, eps_fast, eps_div, n, minmax2,
+                                                                                                   num_bits, symmetric, ok_dev);
+  DFQ_CUDA(cudaGetLastError());
   return 0;
 }

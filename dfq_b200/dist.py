@@ -66,18 +66,20 @@ def partition_lpt(costs: Sequence[int], world: int) -> List[int]:
     return owner
 
 
-def _replay_exit_rule(diffs: Sequence[float], converge_thres: float, converge_count: int) -> int:
-    """dfq.py:81-115 on a recorded sequence of diff_tmp values -> number of sweeps the reference would run
-    (len(diffs) if the rule did not fire within the recording)."""
-    diff, count = 10, 0
-    for n, d in enumerate(diffs, 1):
-        if abs(diff - d) > 1e-9:
-            count, diff = 0, d
+def _replay_exit_rule(diffs: Sequence[float], converge_thres: float, converge_count: int, state=None):
+    """dfq.py:81-115 on a recorded sequence of diff_tmp values -> number of sweeps the reference would run, or None when
+    the rule has not fired by the end of the recording.  `state` ([diff, count, sweeps so far]) carries the rule across
+    consecutive recordings (the kernel records 64 sweeps per launch)."""
+    st = state if state is not None else [10, 0, 0]
+    for d in diffs:
+        st[2] += 1
+        if abs(st[0] - d) > 1e-9:
+            st[1], st[0] = 0, d
         else:
-            count += 1
-        if not (diff > converge_thres and count < converge_count):
-            return n
-    return len(diffs)
+            st[1] += 1
+        if not (st[0] > converge_thres and st[1] < converge_count):
+            return st[2]
+    return None
 
 
 def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8, 1e8), converge_thres=2e-7,
@@ -137,20 +139,29 @@ def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8,
                 plan = sess.plan_cle(local)
                 sess._ensure_room()
                 snapshot = sess.arena.clone()
-                rec = sess.run_cle_plan(plan, s_range, 0.0, 1 << 30, signed, eps, max_sweeps=max_record)
-                local_diffs = torch.zeros(max_record, dtype=torch.float64, device=sess.device)
-                local_diffs[:len(rec.diffs)] = torch.tensor(rec.diffs, dtype=torch.float64, device=sess.device)
-                sess.arena.copy_(snapshot)
             else:
                 raise ValueError(mode)
         else:
             plan = None
-            local_diffs = torch.zeros(max_record, dtype=torch.float64, device=sess.device)
         if mode == "exact":
-            if world > 1:
-                dist.all_reduce(local_diffs, group=group)            # the global dfq.py:105-108 metric per sweep
-            sweeps = _replay_exit_rule(local_diffs.tolist(), converge_thres, converge_count)
+            # Record the shard's metric in launches of `max_record` (<= 64, what DfqCleResult.diffs holds) sweeps that
+            # continue from each other, reduce every recording over the ranks and replay the reference's exit rule on the
+            # global sequence until it fires - however many sweeps that takes (the kernel's own safety net is 4096).
+            max_record = max(1, min(int(max_record), 64))
+            rule, sweeps = [10, 0, 0], None
+            while sweeps is None:
+                local_diffs = torch.zeros(max_record, dtype=torch.float64, device=sess.device)
+                if plan is not None:
+                    rec = sess.run_cle_plan(plan, s_range, 0.0, 1 << 30, signed, eps, max_sweeps=max_record)
+                    local_diffs[:len(rec.diffs)] = torch.tensor(rec.diffs, dtype=torch.float64, device=sess.device)
+                if world > 1:
+                    dist.all_reduce(local_diffs, group=group)        # the global dfq.py:105-108 metric per sweep
+                sweeps = _replay_exit_rule(local_diffs.tolist(), converge_thres, converge_count, rule)
+                if sweeps is None and rule[2] >= 4096:
+                    raise RuntimeError("sharded equalization: the exit rule of dfq.py:81-115 did not fire within 4096 sweeps "
+                                       "(last metric %g)" % rule[0])
             if plan is not None:
+                sess.arena.copy_(snapshot)
                 sess.run_cle_plan(plan, s_range, 0.0, 1 << 30, signed, eps, max_sweeps=sweeps)
         if plan is not None:
             for i, off in zip(mine, plan["s_offs"]):
@@ -177,6 +188,98 @@ def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8,
             S = S_all[i, :chan[i]].clone()
             rr.set_scale_vec(S if graph[rr.get_idxs()[0]].weight.is_cuda else S.cpu())
         return dict(owner=owner, chains=chains, sweeps=sweeps)
+
+
+def sharded_bias_correction(graph, bottoms, targ_type, bits_weight=8, bn_type=torch.nn.BatchNorm2d, signed=False, group=None,
+                            replicate_below: int = 1 << 23):
+    """bias_correction (dfq.py:173-293) with the heavy part - one pass over every corrected weight - sharded over ranks.
+
+    The recurrence of the pass (a layer's expectation reads the fake_bias the previous corrected layer's -delta landed
+    in, dfq.py:204-206,239,293) orders the layers into dependency LEVELS (graphwalk.bias_correction_recipe); layers of one
+    level are independent.  Per level:
+      * a level with fewer than `replicate_below` weight elements (every level of a serial network such as MobileNetV2) is
+        computed by EVERY rank on its replica: the kernel is deterministic, so all ranks hold identical bits and nothing is
+        exchanged;
+      * a larger level is split over the ranks (LPT by weight elements); ONE all_gather_into_tensor of a padded buffer then
+        carries, for every layer of the level, its corrected bias and the updated fake_bias of the BN that follows
+        (SURVEY 8(e) "Collective"), and every rank copies in the rows it did not compute.
+    Every rank must call it with the same (already equalized) model; every rank's model ends up fully corrected.
+    Returns dict(levels=..., sharded_levels=..., owner={layer key: rank})."""
+    from .dfq import _zero_bias
+    from .graphwalk import bias_correction_recipe
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    with torch.no_grad():
+        recipe = bias_correction_recipe(graph, bottoms, targ_type, bn_type)
+        if not recipe:
+            return dict(levels=0, sharded_levels=0, owner={})
+        sess = Session()
+        bn_bound: Dict[object, Tuple[int, int]] = {}
+
+        def bn_offsets(key):
+            if key not in bn_bound:
+                bn = graph[key]
+                bn_bound[key] = (sess.bind(bn.fake_weight), sess.bind(bn.fake_bias))
+            return bn_bound[key]
+
+        items = []
+        for step in recipe:
+            mod = graph[step["layer"]]
+            if mod.bias is None:
+                _zero_bias(mod)                                       # dfq.py:290-291
+            li = sess.add_layer(mod.weight, mod.bias, weight_writeback=False)
+            terms = []
+            for t in step["terms"]:
+                ow, ob = bn_offsets(t["bn"])
+                terms.append(dict(bn_w_off=ow, bn_b_off=ob, n=graph[t["bn"]].fake_bias.numel(), relu=t["relu"], op=t["op"]))
+            nxt = bn_offsets(step["next_bn"])[1] if step["next_bn"] is not None else -1
+            items.append(dict(layer=li, signed=signed, level=0, next_bn_b_off=nxt, terms=terms, key=step["layer"],
+                              numel=mod.weight.numel(), rows=mod.weight.size(0), lev=step["level"]))
+        levels = sorted({it["lev"] for it in items})
+        # ---- plan every launch before the arena is materialised (scratch is part of it) -------------------------------
+        schedule, owner_of = [], {}
+        for lev in levels:
+            its = [it for it in items if it["lev"] == lev]
+            shard = world > 1 and len(its) >= 2 and sum(it["numel"] for it in its) >= replicate_below
+            if shard:
+                own = partition_lpt([it["numel"] for it in its], world)
+                mine = [it for it, o in zip(its, own) if o == rank]
+            else:
+                own, mine = [rank] * len(its), its
+            for it, o in zip(its, own):
+                owner_of[it["key"]] = o if shard else -1              # -1: replicated
+            plan = sess.plan_bias_correct(mine) if mine else None
+            schedule.append((its, own, shard, plan))
+        sess.upload()
+        n_sharded = 0
+        for its, own, shard, plan in schedule:
+            if plan is not None:
+                sess.run_bias_correct_plan(plan, 8)                   # quirk Q2 (dfq.py:218): always 8 bits
+            if not shard:
+                continue
+            n_sharded += 1
+            slot = max(it["rows"] for it in its)
+            per_rank = [[it for it, o in zip(its, own) if o == r] for r in range(world)]
+            cap = max(len(p) for p in per_rank)
+            send = torch.zeros(cap, 2, slot, dtype=torch.float32, device=sess.device)
+            for k, it in enumerate(per_rank[rank]):
+                l = sess.layer(it["layer"])
+                send[k, 0, :it["rows"]] = sess.view(l["bias_off"], it["rows"])
+                if it["next_bn_b_off"] >= 0:
+                    send[k, 1, :it["rows"]] = sess.view(it["next_bn_b_off"], it["rows"])
+            recv = torch.empty(world * cap * 2 * slot, dtype=torch.float32, device=sess.device)
+            dist.all_gather_into_tensor(recv, send.reshape(-1), group=group)
+            recv = recv.view(world, cap, 2, slot)
+            for r in range(world):
+                if r == rank:
+                    continue
+                for k, it in enumerate(per_rank[r]):
+                    l = sess.layer(it["layer"])
+                    sess.view(l["bias_off"], it["rows"]).copy_(recv[r, k, 0, :it["rows"]])
+                    if it["next_bn_b_off"] >= 0:
+                        sess.view(it["next_bn_b_off"], it["rows"]).copy_(recv[r, k, 1, :it["rows"]])
+        sess.download()
+        return dict(levels=len(levels), sharded_levels=n_sharded, owner=owner_of)
 
 
 def sync_observers(model: nn.Module, group=None) -> int:

@@ -48,6 +48,7 @@ class _Bound:
     n: int
     tensor: Optional[torch.Tensor]   # host/device tensor mirrored at [off, off+n); None = scratch
     writeback: bool = True
+    upload: bool = True              # False: an output-only mirror (results land in it at download; nothing to send)
 
 
 class Session:
@@ -59,6 +60,8 @@ class Session:
         self.device = torch.device(device) if device is not None else _default_device()
         self._n = 0
         self._bound: List[_Bound] = []
+        self._by_storage: Dict[tuple, _Bound] = {}     # (data_ptr, numel, device) -> its one mirror in the arena
+        self._xfer = None                               # cached copy lists of upload()/download(), dropped by bind()
         self._layers: List[dict] = []
         self.arena: Optional[torch.Tensor] = None
         self._staging: Optional[torch.Tensor] = None
@@ -72,13 +75,33 @@ class Session:
         self._n = off + int(n)
         return off
 
-    def bind(self, t: torch.Tensor, writeback: bool = True) -> int:
-        """Mirror tensor `t` (fp32, any device) in the arena; returns its offset."""
+    def bind(self, t: torch.Tensor, writeback: bool = True, upload: bool = True) -> int:
+        """Mirror tensor `t` (fp32, any device) in the arena; returns its offset.  A tensor that is bound twice (one
+        module reached from two places of a graph, a conv feeding two BNs, ...) gets ONE mirror: the passes then update it one
+        after the other like the reference updates the one parameter, instead of two copies racing at write-back."""
         if t.dtype != torch.float32:
             raise DfqError("calibration tensors must be float32, got %s" % t.dtype)
+        key = (t.data_ptr(), t.numel(), str(t.device)) if t.numel() else None
+        hit = self._by_storage.get(key) if key is not None else None
+        if hit is not None and hit.tensor is not None and hit.tensor.shape == t.shape and hit.tensor.stride() == t.stride():
+            if (writeback and not hit.writeback) or (upload and not hit.upload):
+                hit.writeback = hit.writeback or writeback
+                hit.upload = hit.upload or upload
+                self._xfer = None
+            return hit.off
         off = self.alloc(t.numel())
-        self._bound.append(_Bound(off, t.numel(), t, writeback))
+        b = _Bound(off, t.numel(), t, writeback, upload)
+        self._bound.append(b)
+        if key is not None:
+            self._by_storage[key] = b
+        self._xfer = None
         return off
+
+    def mirror(self, off: int, t: torch.Tensor):
+        """Make host/device tensor `t` an output-only mirror of the already planned arena range [off, off+numel): the
+        range's contents are written into `t` at download() (e.g. scratch that holds a result, like Relation.S)."""
+        self._bound.append(_Bound(int(off), t.numel(), t, True, False))
+        self._xfer = None
 
     def add_layer(self, weight: torch.Tensor, bias: Optional[torch.Tensor], weight_writeback: bool = True) -> int:
         """Register a Conv2d ([O,J,k,k]) or Linear ([O,J]) weight and its bias (None -> zeros scratch)."""
@@ -109,6 +132,7 @@ class Session:
         l = self._layers[li]
         assert not l["has_bias"] and bias.numel() == l["rows"]
         self._bound.append(_Bound(l["bias_off"], l["rows"], bias, True))
+        self._xfer = None
         l["has_bias"] = True
 
     # ---- materialise / move data --------------------------------------------------------------------
@@ -127,59 +151,81 @@ class Session:
             grown[: self.arena.numel()].copy_(self.arena)
             self.arena = grown
 
+    @staticmethod
+    def _runs(bounds):
+        """Coalesce [off, off+n) of `bounds` (sorted by offset) into copy runs; only alignment padding (< 4 floats) between
+        two mirrors may be swallowed by a run - anything wider is scratch that must keep its device value."""
+        runs = []
+        for b in bounds:
+            if runs and b.off - runs[-1][1] < 4:
+                runs[-1][1] = max(runs[-1][1], b.off + b.n)
+            else:
+                runs.append([b.off, b.off + b.n])
+        return runs
+
+    def _transfer_lists(self):
+        """(span_lo, h2d runs, h2d staging views, h2d sources, d2h runs, d2h staging views, d2h destinations, non-contiguous
+        d2h, device-resident uploads, device-resident write-backs) - built once per binding set: upload()/download() of a
+        whole model are then a handful of calls (torch._foreach_copy_ + one copy per run) instead of a Python loop per tensor."""
+        if self._xfer is not None:
+            return self._xfer
+        host = sorted((b for b in self._bound if b.tensor is not None and not b.tensor.is_cuda and b.n), key=lambda b: b.off)
+        up = [b for b in host if b.upload]
+        down = [b for b in host if b.writeback]
+        lo = min((b.off for b in host), default=0)
+        hi = max((b.off + b.n for b in host), default=0)
+        if host and (self._staging is None or self._staging.numel() < hi - lo):
+            self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=_PIN)
+        st = self._staging
+        x = dict(lo=lo, hi=hi,
+                 h2d_runs=self._runs(up), h2d_dst=[st[b.off - lo: b.off - lo + b.n] for b in up],
+                 h2d_bounds=up,
+                 d2h_runs=self._runs(down),
+                 d2h_src=[st[b.off - lo: b.off - lo + b.n] for b in down], d2h_bounds=down,
+                 dev_up=[b for b in self._bound if b.tensor is not None and b.tensor.is_cuda and b.upload and b.n],
+                 dev_down=[b for b in self._bound if b.tensor is not None and b.tensor.is_cuda and b.writeback and b.n])
+        self._xfer = x
+        return x
+
     def upload(self):
-        """Copy every bound tensor into the arena: host tensors through ONE pinned staging buffer and
-        one H2D copy, device tensors with device-to-device copies."""
+        """Copy every bound tensor into the arena: host tensors through ONE pinned staging buffer and one H2D copy per
+        run of adjacent mirrors (a whole model: one), device tensors with device-to-device copies."""
         self._ensure_room()
-        host = [b for b in self._bound if b.tensor is not None and not b.tensor.is_cuda]
-        if host:
-            lo = min(b.off for b in host)
-            hi = max(b.off + b.n for b in host)
-            if self._staging is None or self._staging.numel() < hi - lo:
-                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=_PIN)
-            st = self._staging
-            # regions between bound tensors carry scratch that must keep its device value: copy only the
-            # bound ranges, coalescing adjacent ones
-            host.sort(key=lambda b: b.off)
-            for b in host:
-                st[b.off - lo: b.off - lo + b.n].copy_(b.tensor.detach().reshape(-1))
-            runs = []
-            for b in host:
-                if runs and _round_up(runs[-1][1], 4) >= b.off and not self._scratch_between(runs[-1][1], b.off):
-                    runs[-1][1] = b.off + b.n
-                else:
-                    runs.append([b.off, b.off + b.n])
-            for a, e in runs:
-                self.arena[a:e].copy_(st[a - lo: e - lo], non_blocking=True)
-                self.h2d_bytes += 4 * (e - a)
-        for b in self._bound:
-            if b.tensor is not None and b.tensor.is_cuda:
+        x = self._transfer_lists()
+        with torch.no_grad():
+            if x["h2d_bounds"]:
+                # (the sources are looked up per call: a caller may have re-pointed a parameter's .data since the last one)
+                torch._foreach_copy_(x["h2d_dst"], [b.tensor.detach().reshape(-1) for b in x["h2d_bounds"]])
+                lo, st = x["lo"], self._staging
+                for a, e in x["h2d_runs"]:
+                    self.arena[a:e].copy_(st[a - lo: e - lo], non_blocking=True)
+                    self.h2d_bytes += 4 * (e - a)
+            for b in x["dev_up"]:
                 self.arena[b.off: b.off + b.n].copy_(b.tensor.detach().reshape(-1))
 
-    def _scratch_between(self, a: int, b: int) -> bool:
-        return b - a >= 4   # only alignment padding (<4 floats) may be overwritten by a coalesced run
-
     def download(self):
-        """Write every bound tensor (writeback=True) back into its original storage, in place."""
-        host = [b for b in self._bound if b.tensor is not None and b.writeback and not b.tensor.is_cuda]
-        if host:
-            lo = min(b.off for b in host)
-            hi = max(b.off + b.n for b in host)
-            if self._staging is None or self._staging.numel() < hi - lo:
-                self._staging = torch.empty(hi - lo, dtype=torch.float32, pin_memory=_PIN)
-            st = self._staging
-            st[: hi - lo].copy_(self.arena[lo:hi], non_blocking=True)
-            if self.arena.is_cuda:
-                torch.cuda.current_stream().synchronize()
-            self.d2h_bytes += 4 * (hi - lo)
-            with torch.no_grad():
-                for b in host:
-                    b.tensor.detach().reshape(-1).copy_(st[b.off - lo: b.off - lo + b.n]) if b.tensor.is_contiguous() \
-                        else b.tensor.detach().copy_(st[b.off - lo: b.off - lo + b.n].reshape(b.tensor.shape))
+        """Write every bound tensor (writeback=True) back into its original storage, in place.  Only the runs that hold
+        write-back mirrors cross PCIe (a pass that leaves the weights alone does not fetch them)."""
+        x = self._transfer_lists()
         with torch.no_grad():
-            for b in self._bound:
-                if b.tensor is not None and b.writeback and b.tensor.is_cuda:
-                    b.tensor.detach().copy_(self.arena[b.off: b.off + b.n].reshape(b.tensor.shape))
+            if x["d2h_runs"]:
+                lo, st = x["lo"], self._staging
+                for a, e in x["d2h_runs"]:
+                    st[a - lo: e - lo].copy_(self.arena[a:e], non_blocking=True)
+                    self.d2h_bytes += 4 * (e - a)
+                if self.arena.is_cuda:
+                    torch.cuda.current_stream().synchronize()
+                dst, src = [], []
+                for b, v in zip(x["d2h_bounds"], x["d2h_src"]):
+                    t = b.tensor.detach()
+                    if t.is_contiguous():
+                        dst.append(t.view(-1)); src.append(v)
+                    else:
+                        t.copy_(v.reshape(t.shape))
+                if dst:
+                    torch._foreach_copy_(dst, src)
+            for b in x["dev_down"]:
+                b.tensor.detach().copy_(self.arena[b.off: b.off + b.n].reshape(b.tensor.shape))
 
     def view(self, off: int, n: int) -> torch.Tensor:
         self._ensure_room()

@@ -233,6 +233,21 @@ class DeviceStack:
         """The mutable region (weights, biases, BN vectors) as one flat view - what a step reads and writes."""
         return self.sess.view(self.w_begin, self.state_floats)
 
+    def block_arrays(self, state: torch.Tensor, b: int):
+        """Block `b` of a flat state image (state() or a saved copy of it) as host numpy arrays: a list of two dicts
+        (conv1, conv2) with w [C,C,k,k], bias, gamma, beta, mean, var, fake_w, fake_b.  Checker-side helper: the parity
+        tests and bench.py's parity_check feed these to the oracle."""
+        C, k = self.C, self.k
+        out = []
+        for li, v in zip(self.layers[2 * b: 2 * b + 2], self.vec[2 * b: 2 * b + 2]):
+            l = self.sess.layer(li)
+            take = lambda off, n: state[off - self.w_begin: off - self.w_begin + n].detach().cpu().numpy().copy()
+            d = dict((n, take(v[n], C)) for n in ("gamma", "beta", "mean", "var", "fake_w", "fake_b"))
+            d["w"] = take(l["w_off"], self.N).reshape(C, C, k, k)
+            d["bias"] = take(l["bias_off"], C)
+            out.append(d)
+        return out
+
     def run(self, converge_thres=2e-7):
         """One calibration step over the whole stack; returns the CleResult."""
         s = self.sess

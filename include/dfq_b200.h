@@ -265,6 +265,14 @@ int dfq_mean_abs_diff(const float* a, const float* b, int64_t n, double* out, vo
 int dfq_quant_error(const float* w, float* eps, int64_t n, const float* minmax2, int num_bits,
                     int symmetric, void* stream);
 
+/* Library self-test hook.  The streaming bias-correction kernel evaluates quantize.py:70-74 without division / rounding
+ * instructions (Markstein-corrected reciprocal product, magic-number rint; dfq_b200/csrc/bc_stream.cuh) when a per-tensor
+ * guard allows it.  This entry computes Q(w) - w of one tensor both ways: eps_fast with that arithmetic, eps_div with the
+ * plain IEEE chain, *ok_dev = the guard's verdict for this tensor's (min, max).  The two arrays must be bit-identical
+ * whenever *ok_dev == 1 (tests/test_gpu_engine.py). */
+int dfq_selftest_bc_arithmetic(const float* w, float* eps_fast, float* eps_div, int64_t n, const float* minmax2,
+                               int num_bits, int symmetric, int* ok_dev, void* stream);
+
 /* x = clamp(x, lo, hi) in place (dfq.py:167-170 clip_weight). */
 int dfq_clamp(float* x, int64_t n, float lo, float hi, void* stream);
 

@@ -146,6 +146,12 @@ def _install_synthetic_data(which):
             def get_annotation(self, i):
                 return self.ids[i], (np.array([[10., 10., 100., 100.]], np.float32), np.array([1], np.int64), np.array([0], np.uint8))
         voc.VOCDataset = VOCDataset
+        # torch >= 2 keeps the strides of the permuted HWC image through `.to(device)` (predictor.py:33-34) and the
+        # reference's observer then fails on `.view(B, -1)` (quantize.py:106); torch 1.1 made that copy contiguous
+        import modeling.detection.transforms.transforms as TT
+        _call = TT.ToTensor.__call__
+        TT.ToTensor.__call__ = lambda self, cvimage, boxes=None, labels=None: (
+            _call(self, cvimage, boxes, labels)[0].contiguous(), boxes, labels)
 
 
 def _cpu_only_shims():

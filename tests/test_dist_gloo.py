@@ -13,6 +13,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+def _nw(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
 def _worker(rank, world, port, mode, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -43,11 +48,6 @@ def _worker(rank, world, port, mode, out_dir):
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **out)
     finally:
         dist.destroy_process_group()
-
-
-def _nw(a, b):
-    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
 @pytest.mark.timeout(900)
@@ -87,6 +87,65 @@ def test_partition_and_chains_are_deterministic():
     # dfq.py:81-115 replay: stops when diff <= thres or after converge_count stagnant sweeps
     assert _replay_exit_rule([1.0, 0.5, 1e-8], 2e-7, 20) == 3
     assert _replay_exit_rule([1.0] * 30, 2e-7, 3) == 4
+    # a recording that ends before the rule fires says so (None) and can be continued by the next recording
+    state = [10, 0, 0]
+    assert _replay_exit_rule([1.0, 0.5, 0.25], 2e-7, 20, state) is None and state[2] == 3
+    assert _replay_exit_rule([0.1, 1e-8, 0.0], 2e-7, 20, state) == 5
+
+
+def _bc_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import torch.nn as nn
+    import fakelib
+    from dfq_b200 import dfq, workload, dist as ddist
+    torch.set_num_threads(2)
+    fakelib.install_plain()
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        targ = [nn.Conv2d, nn.Linear]
+        out = {}
+        # (a) a serial network: every level replicated, nothing exchanged; (b) 6 independent blocks in ONE level, sharded
+        for tag, topo, kw in (("mbv2", workload.load_topology(os.path.join(GOLD, "topology_mobilenetv2.json")), {}),
+                              ("stack", workload.stack_topology(6, channels=48, k=3), dict(replicate_below=1))):
+            def prepared():
+                graph, bottoms, _ = workload.build_graph(topo, seed=4)
+                for m in graph.values():
+                    if isinstance(m, nn.BatchNorm2d):
+                        m.register_buffer("fake_weight", m.weight.detach().abs().clone())
+                        m.register_buffer("fake_bias", m.bias.detach().clone())
+                return graph, bottoms
+            ga, ba = prepared()
+            dfq.bias_correction(ga, ba, targ)                      # what one process computes
+            gb, bb = prepared()
+            info = ddist.sharded_bias_correction(gb, bb, targ, **kw)
+            out[tag + "_sharded_levels"] = np.array(info["sharded_levels"])
+            out[tag + "_owners"] = np.array(sorted(set(info["owner"].values())))
+            worst = 0.0
+            for (ka, ma), (kb, mb) in zip(ga.items(), gb.items()):
+                if type(ma) in targ and ma.bias is not None:
+                    assert mb.bias is not None
+                    worst = max(worst, _nw(mb.bias.detach().numpy(), ma.bias.detach().numpy()))
+                    assert np.array_equal(ma.weight.detach().numpy(), mb.weight.detach().numpy())
+                if hasattr(ma, "fake_bias") and not isinstance(ma, str):
+                    worst = max(worst, _nw(mb.fake_bias.numpy(), ma.fake_bias.numpy()))
+            out[tag + "_worst"] = np.array(worst)
+        np.savez(os.path.join(out_dir, "bc%d.npz" % rank), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_sharded_bias_correction(tmp_path):
+    """sharded_bias_correction: both ranks end with the biases / fake_bias vectors a single process computes - bit for bit
+    (the replicated levels run the same deterministic code, the sharded level copies the owner's rows)."""
+    port = 29500 + (os.getpid() % 2000) + 41
+    mp.spawn(_bc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        d = np.load(tmp_path / ("bc%d.npz" % r))
+        assert float(d["mbv2_worst"]) == 0.0 and float(d["stack_worst"]) == 0.0, (r, float(d["mbv2_worst"]), float(d["stack_worst"]))
+        assert int(d["mbv2_sharded_levels"]) == 0 and d["mbv2_owners"].tolist() == [-1]
+        assert int(d["stack_sharded_levels"]) == 1 and d["stack_owners"].tolist() == [0, 1]
 
 
 def _observer_worker(rank, world, port, out_dir):

@@ -181,7 +181,20 @@ def test_quantize_tensors_bit_exact(bits, sym):
         assert np.array_equal(t.numpy(), r.reshape(t.shape))
 
 
-def test_bias_correct_chain_matches_oracle():
+BC_VARIANTS = ["engine", "stream"]     # k_bc_engine (small, latency-bound models) / k_bc_stream (large phases)
+
+
+def _force_bc_variant(monkeypatch, variant):
+    monkeypatch.setenv("DFQ_BC_STREAM", "1" if variant == "stream" else "0")
+
+
+@pytest.mark.parametrize("variant", BC_VARIANTS)
+def test_bias_correct_chain_matches_oracle(variant, monkeypatch):
+    _force_bc_variant(monkeypatch, variant)
+    _bias_correct_chain()
+
+
+def _bias_correct_chain():
     """conv1+BN1+ReLU -> conv2+BN2 -> conv3 (no ReLU between 2 and 3): two corrected layers in series; the second
     one reads the fake_bias the first one just updated."""
     from dfq_b200.engine import Session
@@ -285,6 +298,26 @@ def test_large_stack_properties():
     assert torch.allclose(sess.view(st.w_begin, 2 * N), before, rtol=1e-6, atol=0)
 
 
+def test_config5_blocks_match_the_oracle():
+    """The headline workload shape itself (BASELINE configs[4]): Conv[512,512,3,3]+BN+ReLU -> Conv[512,512,3,3]+BN blocks
+    through the fused step bench.py times (fold with column scan -> equalization -> correction with range hints) vs the
+    oracle on the same bits: weights / first bias / BN vectors bit-exact, corrected bias within 1e-5, 2 sweeps."""
+    from dfq_b200.engine import Session
+    from dfq_b200.workload import DeviceStack
+    from oracle import stack_check
+    sess = Session()
+    st = DeviceStack(sess, 3, 512, 3, seed=77)
+    st.generate()
+    pristine = st.state().clone()
+    res = st.run()
+    assert res.converged
+    after = st.state()
+    for b in (0, 2):
+        r = stack_check.compare_block(st.block_arrays(pristine, b), st.block_arrays(after, b))
+        assert r["weights_bit_exact"] and r["vectors_bit_exact"], (b, r)
+        assert r["bias_normwise"] < 1e-5 and r["sweeps"] == int(res.group_sweeps[b]) == 2, (b, r, res.group_sweeps)
+
+
 FUSED_CHAINS = CHAINS + [
     [(24, 16, 3, 3), (12, 24, 32, 32)],        # second layer with rows longer than a stage (9216 floats): direct path
     [(33, 7, 3, 3), (21, 33, 3, 3)],           # unaligned tiles (297-float rows at odd offsets): cooperative path
@@ -360,7 +393,13 @@ def test_fused_fold_scan_and_range_hints_equal_the_unfused_calls(shapes):
         assert np.array_equal(x, y)
 
 
-def test_bias_correction_codes_at_rounding_boundaries_are_the_references():
+@pytest.mark.parametrize("variant", BC_VARIANTS)
+def test_bias_correction_codes_at_rounding_boundaries_are_the_references(variant, monkeypatch):
+    _force_bc_variant(monkeypatch, variant)
+    _codes_at_rounding_boundaries()
+
+
+def _codes_at_rounding_boundaries():
     """Weights placed ON and within a few ulps of every rounding boundary of the 8-bit grid must give the reference's codes
     (true IEEE division, clamp, round-half-even - quantize.py:70-74): with E[x] = 1 the row's delta is sum(eps) in fp64, so a
     single wrong code shows as an error of one quantization step."""
@@ -395,6 +434,118 @@ def test_bias_correction_codes_at_rounding_boundaries_are_the_references():
     step = np.float32(scale)
     assert np.abs(d_gpu.astype(np.float64) - d_ref.astype(np.float64)).max() < 1e-3 * step, \
         "a code differs from the reference's (error in quantization steps: %g)" % (np.abs(d_gpu - d_ref).max() / step)
+
+
+@pytest.mark.parametrize("variant", BC_VARIANTS)
+def test_bias_correct_variants_on_mixed_layer_kinds(variant, monkeypatch):
+    """Both bias-correction kernels on every tile kind of the row pipe in one call: 3x3 dense rows (several rows per tile),
+    depthwise (cols = 1, groups = C: one expectation value per row), pointwise with more than 512 columns (expectation
+    read from global memory), the 27-float rows of a first conv (tiles the TMA unit cannot move), rows longer than a
+    stage (processed in global memory), a 'cat' of two BNs and an 'add' of two BNs, signed and unsigned, the raw-sum
+    (bias absorption) flags - against the oracle, 1e-5 normwise, with and without column-extrema hints."""
+    from dfq_b200.engine import Session
+    _force_bc_variant(monkeypatch, variant)
+    g = torch.Generator().manual_seed(31)
+    R = lambda *s: torch.randn(*s, generator=g)
+    bnA = (torch.rand(64, generator=g) + 0.4, R(64) * 0.5)       # feeds 64-channel inputs
+    bnB = (torch.rand(40, generator=g) + 0.4, R(40) * 0.5)
+    bnC = (torch.rand(24, generator=g) + 0.4, R(24) * 0.5)
+    bnD = (torch.rand(3, generator=g) + 0.4, R(3) * 0.5)
+    bnE = (torch.rand(640, generator=g) + 0.4, R(640) * 0.5)
+    bnF = (torch.rand(1200, generator=g) + 0.4, R(1200) * 0.5)
+    cases = [  # (weight, signed, terms, flags)
+        (R(48, 64, 3, 3) * 0.1, False, [("A", True, "set")], {}),
+        (R(64, 1, 3, 3) * 0.3, False, [("A", True, "set")], {}),                          # depthwise
+        (R(36, 640, 1, 1) * 0.05, True, [("E", False, "set")], {}),                        # 640 columns: no register cache
+        (R(16, 3, 3, 3) * 0.4, False, [("D", False, "set")], {}),                          # 27-float rows
+        (R(6, 1200, 2, 2) * 0.02, False, [("F", True, "set")], {}),                        # 4800-float rows: direct
+        (R(20, 64, 1, 1) * 0.2, False, [("B", True, "set"), ("C", False, "cat")], {}),     # cat: 40 + 24
+        (R(20, 64, 1, 1) * 0.2, True, [("A", True, "set"), ("A", False, "add")], {}),      # add
+        (R(12, 32, 3, 3) * 0.1, False, [("A", True, "set")], {}),                          # grouped: 2 groups x 32 columns
+        (R(30, 64, 3, 3) * 0.1, False, [("A", False, "set")], dict(raw_sum=True, add=True)),
+    ]
+    bns = dict(A=bnA, B=bnB, C=bnC, D=bnD, E=bnE, F=bnF)
+    sess = Session()
+    off = {k: (sess.bind(v[0], False), sess.bind(v[1], False)) for k, v in bns.items()}
+    items, biases, lids = [], [], []
+    for w, signed, terms, flags in cases:
+        b = R(w.shape[0])
+        biases.append(b.clone())
+        li = sess.add_layer(w, b)
+        lids.append(li)
+        items.append(dict(layer=li, signed=signed, level=0, next_bn_b_off=-1,
+                          terms=[dict(bn_w_off=off[k][0], bn_b_off=off[k][1], n=bns[k][0].numel(), relu=relu, op=op) for k, relu, op in terms],
+                          **flags))
+    sess.upload()
+    doffs = sess.run_bias_correct(items)
+    for (w, signed, terms, flags), b0, li, doff in zip(cases, biases, lids, doffs):
+        ex = None
+        for k, relu, op in terms:
+            v = O.relu_expectation(bns[k][0].numpy(), bns[k][1].numpy()) if relu else bns[k][1].numpy().copy()
+            ex = v if ex is None else (np.concatenate([ex, v]) if op == "cat" else ex + v)
+        if flags.get("raw_sum"):
+            d = O.bias_absorb_wc(w.numpy(), ex, ex.shape[0])
+            want = b0.numpy() + d
+        else:
+            d = O.bias_delta(w.numpy(), ex, signed=signed)
+            want = b0.numpy() + (-d)
+        got_d = sess.view(doff, w.shape[0]).cpu().numpy()
+        got_b = sess.view(sess.layer(li)["bias_off"], w.shape[0]).cpu().numpy()
+        assert _normwise(got_d, d) < 1e-5, (tuple(w.shape), signed, terms, _normwise(got_d, d))
+        assert _normwise(got_b, want) < 1e-5, (tuple(w.shape), "bias")
+
+
+def test_bc_fast_quotient_equals_ieee_division():
+    """dfq_selftest_bc_arithmetic: the XU-free arithmetic of k_bc_stream (Markstein-corrected reciprocal product instead of
+    div.rn, magic-number rint) must give Q(w) - w bit-identical to the IEEE chain of quantize.py:70-74 whenever its
+    per-tensor guard says so - over thousands of (min, max) pairs x numerators that sit ON and within 4 ulps of every
+    half-integer quotient plus dense random ones; and the guard must refuse scales with an all-ones mantissa."""
+    import ctypes as C
+    from dfq_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    n_ok = n_refused = 0
+    bad = []
+    for trial in range(1500):
+        signed = trial % 5 == 4
+        bits = 8 if trial % 7 else (4, 16)[trial % 2]
+        mag = 10.0 ** rng.uniform(-6, 4) if trial % 101 else 1e-31      # tiny ranges: outside the exponent window -> refused
+        lo = np.float32(-mag * rng.uniform(0.1, 1.0)) if trial % 3 else np.float32(mag * rng.uniform(0.0, 0.5))
+        hi = np.float32(float(lo) + mag * rng.uniform(0.2, 2.0))
+        if trial % 97 == 0:      # force an all-ones mantissa scale: (hi - lo) / 255 == 0x..7fffff
+            s = np.uint32((np.float32(mag).view(np.uint32) & np.uint32(0xff800000)) | np.uint32(0x7fffff)).view(np.float32)
+            lo = np.float32(0.0); hi = np.float32(float(s) * 255.0)
+        qmax = (2 ** (bits - 1) - 1) if signed else (2 ** bits - 1)
+        scale = (max(abs(float(hi)), abs(float(lo))) / qmax) if signed else (float(hi) - float(lo)) / qmax
+        mn = 0.0 if signed else float(lo)
+        ks = np.arange(-(2 ** (bits - 1)) - 1 if signed else -1, qmax + 2, max(1, (qmax + 3) // 300))
+        vals = []
+        for k in ks:
+            b = np.float32(mn + (k + 0.5) * scale)
+            v_up = v_dn = b
+            vals.append(b)
+            for _ in range(4):
+                v_up = np.nextafter(v_up, np.float32(np.inf), dtype=np.float32); v_dn = np.nextafter(v_dn, np.float32(-np.inf), dtype=np.float32)
+                vals.append(v_up); vals.append(v_dn)
+        vals = np.concatenate([np.array(vals, np.float32), rng.uniform(float(lo), float(hi), 4096).astype(np.float32),
+                               np.array([lo, hi, 0.0, np.nextafter(lo, np.float32(np.inf), dtype=np.float32)], np.float32)])
+        vals = np.clip(vals, lo, hi)
+        w = torch.from_numpy(vals).cuda()
+        mm = torch.tensor([float(lo), float(hi)], dtype=torch.float32, device="cuda")
+        ef = torch.empty_like(w); ed = torch.empty_like(w); ok = torch.zeros(1, dtype=torch.int32, device="cuda")
+        P = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.dfq_selftest_bc_arithmetic(P(w), P(ef), P(ed), w.numel(), P(mm), bits, 1 if signed else 0, P(ok), _lib.stream_ptr()),
+                   "dfq_selftest_bc_arithmetic")
+        ref = O.quantize(vals, bits, float(lo), float(hi), signed) - vals
+        assert np.array_equal(ed.cpu().numpy(), ref), "IEEE chain differs from the oracle"
+        if int(ok.item()):
+            n_ok += 1
+            if not torch.equal(ef, ed):
+                bad.append((trial, float(lo), float(hi), bits, signed, int((ef != ed).sum())))
+        else:
+            n_refused += 1
+    assert not bad, bad[:5]
+    assert n_ok > 1300 and n_refused >= 10, (n_ok, n_refused)      # 15 tiny-range trials + the all-ones mantissas that survive rounding
 
 
 def test_invalid_descriptors_are_rejected_with_a_message_not_a_crash():

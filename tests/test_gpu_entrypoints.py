@@ -271,6 +271,8 @@ def test_update_quant_range_drives_every_observer_and_pins_the_input_range():
     ops = [QuantMeasure(num_bits=8, momentum=0.1) for _ in range(2)]
     LT.module_tensor_op = LT.CustomTensorOP(ops, record)
     model.add_module("custom_tensor_op", LT.module_tensor_op)
+    model.eval()     # (in main_cls.py the op observers are added after model.eval() and stay in training mode - EMA on top,
+    #                   quantize.py:109-113 - until the final model.eval(); here every observer is in eval mode)
     graph = OrderedDict([("Data", "Data"), (1, model.c1), (2, model.c2), ("add_9", "add_9")])
     bottoms = OrderedDict([("Data", None), (1, ["Data"]), (2, [1]), ("add_9", [1, 2])])
     g = torch.Generator().manual_seed(3)

@@ -299,3 +299,19 @@ def bias_correction_fixture(name):
 if __name__ == "__main__" and "bc" in sys.argv[1:]:
     bias_correction_fixture("resnet18")
     bias_correction_fixture("mobilenetv2")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def ncnn_table_rows():
+    """The 53 + 53 scale values of the reference's checked-in table (modeling/ncnn/model_quant_relu_equal.table): rows 1-53
+    `<layer>_param_0 s s s ...` (first value = 128/max|W|), rows 54-106 `<layer> s` (activation scale)."""
+    rows = [l.split() for l in open(os.path.join(refenv.REF_ROOT, "modeling", "ncnn", "model_quant_relu_equal.table")).read().strip().splitlines()]
+    assert len(rows) == 106
+    np.savez_compressed(os.path.join(GOLD, "ncnn_table_rows.npz"), weight_scales=np.array([float(r[1]) for r in rows[:53]]),
+                        activation_scales=np.array([float(r[1]) for r in rows[53:]]),
+                        names=np.array([r[0] for r in rows[53:]]))
+    print("ncnn table rows: 53 + 53")
+
+
+if __name__ == "__main__" and "table" in sys.argv[1:]:
+    ncnn_table_rows()
