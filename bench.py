@@ -51,6 +51,10 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-mbv2", action="store_true")
     p.add_argument("--no-parity-check", action="store_true")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="which curve is the line's headline `value` (the other one is reported next to it): weak = --layers "
+                        "pairs PER GPU, strong = --layers pairs IN TOTAL split over the GPUs (SURVEY 8(d) config 5)")
+    p.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement")
     return p.parse_args()
 
 
@@ -148,6 +152,35 @@ def cpu_pipeline(n_pairs, seed=1234, eager=False):
             layers[1].b = layers[1].b + (-d)
             bns[1] = (bns[1][0], bns[1][1] + (-d))
     return time.perf_counter() - t0, sweeps
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore its page-locked buffers: first touch) to the NUMA node its GPU hangs off.  Round 1's
+    e2e arm scaled 0.67 / 0.49 at 4 / 8 GPUs because every rank allocated its pinned staging memory wherever the launcher
+    happened to start it (GPUs 4-7 sit on node 1).  Returns dict(node, cpus) or None when the topology is not exposed."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        if hasattr(p, "pci_bus_id") and hasattr(p, "pci_device_id"):
+            dev = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        else:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            dev = out[-12:] if len(out) >= 12 else out
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % dev).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
 
 
 def one_socket_cores():
@@ -249,15 +282,22 @@ def mobilenetv2_latency(dev, reps=5):
     t0 = time.perf_counter()
     cal = GraphCalibration(graph, bottoms, targ, device=dev)
     plan_ms = (time.perf_counter() - t0) * 1e3
-    e2e, devms, sweeps = [], [], 0
+    e2e, devms, sweeps, parts = [], [], 0, []
     for i in range(reps + 2):
         restore()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = cal.run(equalize=True, correction=True)
+        cal.upload()
+        t1 = time.perf_counter()
+        cal.run_device(equalize=True, correction=True)
+        t2 = time.perf_counter()
+        cal.download()
         torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        res = cal.last_cle
         if i >= 2:
-            e2e.append((time.perf_counter() - t0) * 1e3)
+            e2e.append((t3 - t0) * 1e3)
+            parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
         sweeps = res.n_sweeps
     restore()
     cal.upload()
@@ -273,6 +313,9 @@ def mobilenetv2_latency(dev, reps=5):
             devms.append(a.elapsed_time(b))
     return {"pairs": pairs, "relations": len(cal.relations), "sweeps": sweeps, "plan_ms": plan_ms,
             "e2e_ms": sorted(e2e)[len(e2e) // 2], "device_ms": sorted(devms)[len(devms) // 2],
+            "e2e_parts_ms": {"stage_and_h2d_enqueue": sorted(p[0] for p in parts)[len(parts) // 2],
+                             "launches_until_results_known": sorted(p[1] for p in parts)[len(parts) // 2],
+                             "d2h_and_write_back": sorted(p[2] for p in parts)[len(parts) // 2]},
             "pairs_per_s_e2e": pairs / (sorted(e2e)[len(e2e) // 2] * 1e-3),
             "what": "BN fold + equalization to convergence + bias correction of MobileNetV2 (random init, seed 0); e2e = "
                     "host parameters -> pinned H2D -> 3 launches -> D2H -> in place"}
@@ -289,6 +332,7 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)          # before any page-locked allocation
     free, total = torch.cuda.mem_get_info()
     layers = args.layers - (args.layers % 2)
     bytes_per_layer = 4 * (N_PER_LAYER + 8 * C)
@@ -307,31 +351,57 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_buf = None
-    if world > 1:
-        s_lo = min(stack.cle_plan["s_offs"]); s_hi = max(stack.cle_plan["s_offs"]) + C
-        gather_buf = torch.empty(world * (s_hi - s_lo), dtype=torch.float32, device=dev)
+    class Exchange:
+        """The path's one exchange (SURVEY 8(e) "Collective"): ONE all-gather of a flat buffer holding, for this rank's
+        shard, the accumulated scale vectors S of every relation, the corrected biases and the BN vectors (fake_weight /
+        fake_bias) of every layer - after it every rank holds the [C]-sized results of the whole job; weights stay put."""
 
-    def step(timers=None):
-        stack.state().copy_(pristine)                       # untimed: restores (and evicts L2: 38 GB >> 126 MB)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        ev[0].record()
-        sess.run_bn_fold(stack.fold_plan)
-        ev[1].record()
-        res = sess.run_cle_plan(stack.cle_plan, cols_ready=stack.fold_plan["scanned"])
-        ev[2].record()
-        sess.run_bias_correct_plan(stack.bc_plan, 8, col_hints=sess.cle_col_hints(stack.cle_plan, res))
-        if stack.quant_plan is not None:
-            sess.run_quantize(stack.quant_plan)
-        ev[3].record()
-        if world > 1:   # the path's one exchange: all-gather of the scale vectors (north_star)
-            dist.all_gather_into_tensor(gather_buf, sess.view(s_lo, s_hi - s_lo))
-        ev[4].record()
-        torch.cuda.synchronize()
-        if timers is not None:
-            timers.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
-        return res
+        def __init__(self, st):
+            self.views = [st.scale_state(), st.channel_state()]
+            self.n = sum(v.numel() for v in self.views)
+            self.send = torch.empty(self.n, dtype=torch.float32, device=dev)
+            self.recv = torch.empty(world * self.n, dtype=torch.float32, device=dev)
 
+        def run(self):
+            o = 0
+            for v in self.views:
+                self.send[o:o + v.numel()].copy_(v); o += v.numel()
+            dist.all_gather_into_tensor(self.recv, self.send)
+
+    def make_step(st, se, saved, xch):
+        def step(timers=None):
+            st.state().copy_(saved)                          # untimed: restores (and evicts L2 when the stack is >> 126 MB)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            se.run_bn_fold(st.fold_plan)
+            ev[1].record()
+            res = se.run_cle_plan(st.cle_plan, cols_ready=st.fold_plan["scanned"])
+            ev[2].record()
+            se.run_bias_correct_plan(st.bc_plan, 8, col_hints=se.cle_col_hints(st.cle_plan, res))
+            if st.quant_plan is not None:
+                se.run_quantize(st.quant_plan)
+            ev[3].record()
+            if xch is not None:
+                xch.run()
+            ev[4].record()
+            torch.cuda.synchronize()
+            if timers is not None:
+                timers.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
+            return res
+        return step
+
+    def measure(step_fn):
+        for _ in range(max(args.warmup, 3)):
+            r = step_fn()
+        barrier()
+        tm = []
+        for _ in range(args.steps):
+            r = step_fn(tm)
+        barrier()
+        return r, tm
+
+    exchange = Exchange(stack) if world > 1 else None
+    step = make_step(stack, sess, pristine, exchange)
     for _ in range(max(args.warmup, 3)):
         res = step()
     barrier()
@@ -364,6 +434,31 @@ def run_b200(args, rank, world, local_rank):
     value = world * layers / (ms_step * 1e-3)
     phases = [sum(r[i] for r in timers) / len(timers) for i in range(4)]
 
+    # ---- strong scaling: the SAME total stack (--layers pairs) split over the ranks -------------------------------------
+    strong = None
+    if world > 1 and not args.no_strong:
+        s_blocks = max(1, (args.layers // 2) // world)
+        s_sess = Session(dev)
+        s_stack = DeviceStack(s_sess, s_blocks, C, K, seed=4321 + rank, quantize=args.quantize)
+        s_stack.generate()
+        s_saved = s_stack.state().clone()
+        s_x = Exchange(s_stack)
+        s_res, s_tm = measure(make_step(s_stack, s_sess, s_saved, s_x))
+        ts = torch.tensor([sum(sum(r) for r in s_tm) / len(s_tm)] + [sum(r[i] for r in s_tm) / len(s_tm) for i in range(4)],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"value": world * 2 * s_blocks / (float(ts[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(ts[0]),
+                  "layers_total": world * 2 * s_blocks, "layers_per_gpu": 2 * s_blocks, "sweeps": s_res.n_sweeps,
+                  "phases_ms_max_over_ranks": {"bn_fold": float(ts[1]), "equalize": float(ts[2]), "bias_correct": float(ts[3]),
+                                               "exchange": float(ts[4])},
+                  "exchange_bytes_per_rank": 4 * s_x.n,
+                  "l2": "%.1f GB of weights per GPU >> 126 MB L2; restored from a pristine copy (untimed) before every step"
+                        % (4e-9 * N_PER_LAYER * 2 * s_blocks),
+                  "what": "fixed total of %d pairs split over %d GPUs; speed-up over the 1-GPU weak line at the same total is "
+                          "strong-scaling efficiency x N" % (world * 2 * s_blocks, world)}
+        del s_stack, s_sess, s_saved, s_x
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     cle_bytes = 8.0 * N_PER_LAYER * layers * res.n_sweeps          # 8 B per weight per sweep
@@ -379,8 +474,8 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_e2e:
         from dfq_b200.workload import HostStackCalibrator
         chunk_blocks = max(1, args.e2e_chunk // 2)                # 32 layer pairs = 302 MB per chunk
-        # pinned host memory is a per-box resource: 2 x 4.8 GB per rank at 512 pairs; keep the box total at what 4 ranks use
-        e2e_pairs = args.e2e_layers if world <= 4 else max(2 * chunk_blocks * 2, args.e2e_layers * 4 // world)
+        # 2 x 4.8 GB of page-locked memory per rank at 512 pairs, allocated on the rank's own NUMA node (bind_to_gpu_numa_node)
+        e2e_pairs = args.e2e_layers
         n_chunks = max(2, min(e2e_pairs, layers) // (2 * chunk_blocks))
         e_layers = n_chunks * 2 * chunk_blocks
         del pristine
@@ -444,9 +539,16 @@ def run_b200(args, rank, world, local_rank):
                        "layers_per_gpu": layers, "weights_bytes_per_gpu": 4 * N_PER_LAYER * layers, "sweeps": res.n_sweeps,
                        "parallelism": "independent blocks sharded over %d rank(s); one all-gather of the scale vectors" % world,
                        "l2": "working set %.1f GB >> 126 MB L2; state restored from a pristine copy (untimed) before every step" % (4e-9 * N_PER_LAYER * layers)},
-            "phases_ms": {"bn_fold": phases[0], "equalize": phases[1], "bias_correct": phases[2], "allgather": phases[3]},
+            "phases_ms": {"bn_fold": phases[0], "equalize": phases[1], "bias_correct": phases[2], "exchange": phases[3]},
+            "exchange": None if exchange is None else {"bytes_per_rank": 4 * exchange.n,
+                                                       "carries": "S of every relation + corrected biases + BN vectors (fake_weight, fake_bias) of every layer, one all_gather_into_tensor"},
+            "strong": strong, "numa": numa,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "mobilenetv2": mbv2, "parity_check": parity}
+    if args.scaling == "strong" and strong is not None:
+        line["weak"] = {"value": line["value"], "ms_per_step": line["ms_per_step"], "layers_per_gpu": layers}
+        line["value"], line["ms_per_step"], line["scaling"] = strong["value"], strong["ms_per_step"], "strong"
+        line["config"]["workload"] = "synthetic stack of %d Conv[512,512,3,3]+BN pairs IN TOTAL split over %d GPUs (BASELINE configs[4])" % (strong["layers_total"], world)
     print(json.dumps(line))
 
 

@@ -102,6 +102,9 @@ SIGNATURES = {
     "dfq_quant_dequant_dev": [_PF, _PF, _I64, _PF, _PF, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _ST],
     "dfq_act_minmax_per_sample": [_PF, _I64, _I64, _PF, _PF, _ST],
     "dfq_observer_update": [_PF, _PF, _PF, C.c_int, C.c_float, _ST],
+    "dfq_observe_quant": [_PF, _PF, _I64, _I64, _PF, _PF, _PF, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _ST],
+    "dfq_bnstat_loss_fwd": [_PF, _I64, _I64, _I64, _PF, _PF, C.c_float, _PF, _PF, C.c_void_p, _ST],
+    "dfq_bnstat_loss_bwd": [_PF, _PF, _I64, _I64, _I64, _PF, _PF, C.c_float, _PF, _PF, _PF, C.c_int, _ST],
     "dfq_range_rows": [_PF, _I64, _I64, _PF, _PF, _ST],
     "dfq_range_cols": [_PF, _I64, _I64, _I64, _I64, _PF, _PF, _ST],
     "dfq_mean_abs_diff": [_PF, _PF, _I64, C.c_void_p, _ST],

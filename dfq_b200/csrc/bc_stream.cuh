@@ -14,13 +14,17 @@
 //     ends with padding SKIP items up to a multiple of 8 and then 8 END items, so every consumer sees exactly one END;
 //   * a tile's rows are reduced by the warp alone (lanes over input columns, 9 taps each, warp shuffle at the end);
 //     lane r requests row r's read-modify-write operands before the tile and retires them after it;
-//   * the expectation vector of the current (layer, group) stays in REGISTERS (cols <= 512: 16 per lane) across tiles;
+//   * the expectation vector of the current (layer, group) is cached per warp in shared memory (cols <= 512) across tiles;
+//   * the row is read with 32-bit shared-memory addresses (ld.shared, no generic LD + 64-bit address arithmetic) in a
+//     ROLLED column loop: the first version unrolled 16 x 9 taps x 5 variants = 23 800 SASS instructions and stalled on
+//     instruction fetch (ncu: no_instruction 1.39 per issue) - profiles/r2_bc_stream_v1.md;
 //   * the quantization error is computed with no XU-pipe instruction:
 //       - the quotient t / scale as Markstein's correction of the product with the correctly rounded reciprocal
 //         (q0 = t*y, r = fma(-q0, s, t), q = fma(r, y, q0); y = __frcp_rn(s)): equal to the IEEE quotient when no
 //         intermediate underflows and the mantissa of s is not all ones - both checked once per tensor (BcFastQuant::ok),
 //         otherwise the plain __fdiv_rn chain runs for that tensor.  t lies in [0, max-min], q in [qmin, qmax];
-//       - rint() for |t| <= 2^22 as (t + 1.5*2^23) - 1.5*2^23 (two FADDs, round-half-even like FRND).
+//       - rint() for |t| <= 2^22 as (t + 1.5*2^23) - 1.5*2^23 (two FADDs, round-half-even like FRND);
+//       - no clamp: on the tensor's own range the quotient cannot leave [qmin, qmax] before the rounding (bc_qerr_own_range).
 //     tests/test_gpu_engine.py::test_bc_fast_quotient_equals_ieee_division checks codes AND quotients against __fdiv_rn
 //     over thousands of scales x dense numerators including every half-integer neighbourhood.
 #pragma once
@@ -29,13 +33,16 @@
 
 namespace dfq {
 
-constexpr int kBcConsumers = 8;
+#ifndef DFQ_BC_CONSUMERS
+#define DFQ_BC_CONSUMERS 8
+#endif
+constexpr int kBcConsumers = DFQ_BC_CONSUMERS;
 constexpr int kBcThreads = (kBcConsumers + 1) * 32;
 #ifndef DFQ_BC_STAGES
 #define DFQ_BC_STAGES 11
 #endif
 constexpr int kBcStages = DFQ_BC_STAGES;
-constexpr int kBcExRegs = 16;                 // expectation values per lane kept in registers (cols <= 512)
+constexpr int kBcExCols = 512;                // expectation values a consumer warp caches in shared memory (2 KB per warp)
 
 enum { TK_SKIP = 3, TK_END = 4 };
 
@@ -94,7 +101,12 @@ struct BcRing {
     }
     __syncthreads();
   }
-  static constexpr size_t smem_bytes() { return (size_t)kBcStages * kStageBytes + 16 * kBcStages + 16 + kBcStages * sizeof(TileDesc) + 64; }
+  // behind the ring: one expectation cache per consumer warp
+  __device__ __forceinline__ float* ex_cache(int warp) const {
+    return (float*)(base + ring_bytes()) + (size_t)warp * kBcExCols;
+  }
+  __host__ __device__ static constexpr size_t ring_bytes() { return (((size_t)kBcStages * kStageBytes + 16 * kBcStages + 16 + kBcStages * sizeof(TileDesc)) + 127) & ~(size_t)127; }
+  static constexpr size_t smem_bytes() { return ring_bytes() + (size_t)kBcConsumers * kBcExCols * 4 + 64; }
 };
 
 // Producer lane: put item `d` at sequence number n.
@@ -110,34 +122,84 @@ __device__ __forceinline__ void bc_produce(BcRing& ring, unsigned long long n, c
   }
 }
 
-// One output row (shared or global memory) against an expectation vector held in registers / global memory.
-template <bool FAST, bool RAW, bool EXREG>
-__device__ __forceinline__ double bc_stream_row(const float* __restrict__ row, int cols, int kk, const float* __restrict__ ex,
-                                                const float (&exr)[kBcExRegs], const BcFastQuant& f, int lane) {
-  double acc = 0.0;
-  if (EXREG) {
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
+// quantize.py:70-74 without the clamp: for a tensor quantized on ITS OWN range (always the case in bias correction,
+// dfq.py:14) t = w - min lies in [0, RN(max - min)] and RN(t / scale) in [0, 255.00003] (symmetric: |q| <= 127.00002), so
+// clamp_(qmin, qmax) never changes anything before the rounding.  (NaN weights propagate, as they do through torch.clamp.)
+__device__ __forceinline__ float bc_qerr_own_range(float w, const BcFastQuant& f) {
+  float t = __fadd_rn(w, f.neg_min);
+  const float q0 = __fmul_rn(t, f.rcp);
+  const float r = __fmaf_rn(-q0, f.scale, t);
+  t = __fmaf_rn(r, f.rcp, q0);
+  t = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+  t = __fmul_rn(t, f.scale);
+  return __fsub_rn(__fadd_rn(t, f.min_v), w);
+}
+
+// One column (kk taps at shared address `a`) of one output row.  MODE 0: XU-free arithmetic on the tensor's own range,
+// 1: plain IEEE chain (per-tensor guard refused), 2: raw sum (bias absorption).
+template <int MODE, int KK>
+__device__ __forceinline__ float bc_col_smem(uint32_t a, int kk, const BcFastQuant& f) {
+  float E = 0.f;
+  if (KK == 9) {
+    float w[9];
 #pragma unroll
-    for (int c = 0; c < kBcExRegs; ++c) {
-      const int j = lane + 32 * c;
-      if (j < cols) {
-        const float* p = row + (size_t)j * kk;
-        float E = 0.f;
-        if (kk == 9) {
+    for (int k = 0; k < 9; ++k) w[k] = lds_f32(a + 4u * k);
 #pragma unroll
-          for (int k = 0; k < 9; ++k) E = __fadd_rn(E, RAW ? p[k] : bc_qerr<FAST>(p[k], f));
-        } else {
-          for (int k = 0; k < kk; ++k) E = __fadd_rn(E, RAW ? p[k] : bc_qerr<FAST>(p[k], f));
-        }
-        acc += (double)E * (double)exr[c];
-      }
-    }
+    for (int k = 0; k < 9; ++k) E = __fadd_rn(E, MODE == 2 ? w[k] : (MODE == 0 ? bc_qerr_own_range(w[k], f) : bc_qerr<false>(w[k], f)));
+  } else if (KK == 1) {
+    const float w = lds_f32(a);
+    E = __fadd_rn(E, MODE == 2 ? w : (MODE == 0 ? bc_qerr_own_range(w, f) : bc_qerr<false>(w, f)));
   } else {
-    for (int j = lane; j < cols; j += 32) {
-      const float* p = row + (size_t)j * kk;
-      float E = 0.f;
-      for (int k = 0; k < kk; ++k) E = __fadd_rn(E, RAW ? p[k] : bc_qerr<FAST>(p[k], f));
-      acc += (double)E * (double)__ldcg(ex + j);
+    for (int k = 0; k < kk; ++k) {
+      const float w = lds_f32(a + 4u * k);
+      E = __fadd_rn(E, MODE == 2 ? w : (MODE == 0 ? bc_qerr_own_range(w, f) : bc_qerr<false>(w, f)));
     }
+  }
+  return E;
+}
+
+// One output row resident in SHARED memory: lanes over input columns (kk taps each, 36-byte lane stride for 3x3: conflict
+// free), fp32 tap sum per column, fp64 dot with the expectation vector (`exs`: this warp's shared-memory copy when the
+// layer has <= kBcExCols columns, else `exg` in global memory).
+template <int MODE, int KK>
+__device__ __forceinline__ double bc_stream_row_smem(uint32_t srow, int cols, int kk, const float* __restrict__ exs,
+                                                     const float* __restrict__ exg, const BcFastQuant& f, int lane) {
+  double acc = 0.0;
+  const int nfull = cols >> 5;
+  const uint32_t stride = 32u * 4u * (uint32_t)kk;
+  uint32_t a = srow + (uint32_t)lane * 4u * (uint32_t)kk;
+  if (exs) {
+#pragma unroll 2
+    for (int c = 0; c < nfull; ++c, a += stride)
+      acc = __fma_rn((double)bc_col_smem<MODE, KK>(a, kk, f), (double)exs[lane + 32 * c], acc);
+    if (lane + 32 * nfull < cols) acc = __fma_rn((double)bc_col_smem<MODE, KK>(a, kk, f), (double)exs[lane + 32 * nfull], acc);
+  } else {
+    for (int c = 0; c < nfull; ++c, a += stride)
+      acc = __fma_rn((double)bc_col_smem<MODE, KK>(a, kk, f), (double)__ldcg(exg + lane + 32 * c), acc);
+    if (lane + 32 * nfull < cols) acc = __fma_rn((double)bc_col_smem<MODE, KK>(a, kk, f), (double)__ldcg(exg + lane + 32 * nfull), acc);
+  }
+  return warp_sum(acc);
+}
+
+// Rows longer than a stage stay in global memory (TK_DIRECT): plain loop, L2 reads.
+template <int MODE>
+__device__ __forceinline__ double bc_stream_row_gmem(const float* __restrict__ row, int cols, int kk, const float* __restrict__ exg,
+                                                     const BcFastQuant& f, int lane) {
+  double acc = 0.0;
+  for (int j = lane; j < cols; j += 32) {
+    const float* p = row + (size_t)j * kk;
+    float E = 0.f;
+    for (int k = 0; k < kk; ++k) {
+      const float w = ldg_stream1(p + k);
+      E = __fadd_rn(E, MODE == 2 ? w : (MODE == 0 ? bc_qerr_own_range(w, f) : bc_qerr<false>(w, f)));
+    }
+    acc = __fma_rn((double)E, (double)__ldcg(exg + j), acc);
   }
   return warp_sum(acc);
 }

@@ -616,10 +616,9 @@ k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
     } else {
       int cur = -1, cur_group = -1, so = 1;
       DfqBcLayer b; DfqLayer l; BcFastQuant f;
-      bool raw = false, exreg = false;
-      float exr[kBcExRegs];
-#pragma unroll
-      for (int c = 0; c < kBcExRegs; ++c) exr[c] = 0.f;
+      int mode = 1;                                  // 0: XU-free arithmetic, 1: IEEE chain, 2: raw sums (bias absorption)
+      bool excached = false;
+      float* exs = ring.ex_cache(warp);
       for (;; n += kBcConsumers) {
         const int s = bc_take(ring, n);
         const TileDesc d = ring.desc[s];
@@ -631,37 +630,49 @@ k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
           f = bc_fast_quant(quant_scalars((double)__ldcg(arena + b.minmax_off), (double)__ldcg(arena + b.minmax_off + 1),
                                           num_bits, b.signed_mode), num_bits);
           so = l.rows / (b.expect_len / l.cols);
-          raw = (b.flags & 1) != 0;
-          exreg = l.cols <= 32 * kBcExRegs;
+          mode = (b.flags & 1) ? 2 : (f.ok ? 0 : 1);
+          excached = l.cols <= kBcExCols;
         }
         const int row_len = l.cols * l.kk;
         if (d.kind == TK_PLAIN) {       // a tile the TMA unit cannot move: the warp fetches it itself
           for (int i = lane; i < d.floats; i += 32) ring.stage(s)[i] = ldg_stream1(d.gptr + i);
           __syncwarp();
         }
-        const float* base = (d.kind == TK_DIRECT) ? d.gptr : ring.stage(s);
         // lane r requests row r's read-modify-write operands before the tile and retires them after it
         float old_bias = 0.f, old_next = 0.f, dl = 0.f;
         if (lane < d.nrows) {
           old_bias = __ldcg(arena + l.bias_off + d.row0 + lane);
           if (b.next_bn_b_off >= 0) old_next = __ldcg(arena + b.next_bn_b_off + d.row0 + lane);
         }
+        const uint32_t sbase = smem_u32(ring.stage(s));
         for (int r = 0; r < d.nrows; ++r) {
           const int g = (d.row0 + r) / so;
           const float* ex = arena + b.expect_off + (size_t)g * l.cols;
-          if (exreg && g != cur_group) {
+          if (excached && g != cur_group) {
             cur_group = g;
-#pragma unroll
-            for (int c = 0; c < kBcExRegs; ++c) { const int j = lane + 32 * c; exr[c] = j < l.cols ? __ldcg(ex + j) : 0.f; }
+            __syncwarp();
+            for (int j = lane; j < l.cols; j += 32) exs[j] = __ldcg(ex + j);
+            __syncwarp();
           }
-          const float* row = base + (size_t)r * row_len;
           double acc;
-          if (raw)            acc = exreg ? bc_stream_row<false, true, true>(row, l.cols, l.kk, ex, exr, f, lane)
-                                          : bc_stream_row<false, true, false>(row, l.cols, l.kk, ex, exr, f, lane);
-          else if (f.ok)      acc = exreg ? bc_stream_row<true, false, true>(row, l.cols, l.kk, ex, exr, f, lane)
-                                          : bc_stream_row<true, false, false>(row, l.cols, l.kk, ex, exr, f, lane);
-          else                acc = exreg ? bc_stream_row<false, false, true>(row, l.cols, l.kk, ex, exr, f, lane)
-                                          : bc_stream_row<false, false, false>(row, l.cols, l.kk, ex, exr, f, lane);
+          if (d.kind == TK_DIRECT) {
+            const float* row = d.gptr + (size_t)r * row_len;
+            acc = mode == 0 ? bc_stream_row_gmem<0>(row, l.cols, l.kk, ex, f, lane)
+                : mode == 1 ? bc_stream_row_gmem<1>(row, l.cols, l.kk, ex, f, lane)
+                            : bc_stream_row_gmem<2>(row, l.cols, l.kk, ex, f, lane);
+          } else {
+            const uint32_t srow = sbase + (uint32_t)r * (uint32_t)row_len * 4u;
+            const float* xs = excached ? exs : nullptr;
+            if (mode == 0) {
+              acc = l.kk == 9 ? bc_stream_row_smem<0, 9>(srow, l.cols, 9, xs, ex, f, lane)
+                  : l.kk == 1 ? bc_stream_row_smem<0, 1>(srow, l.cols, 1, xs, ex, f, lane)
+                              : bc_stream_row_smem<0, 0>(srow, l.cols, l.kk, xs, ex, f, lane);
+            } else if (mode == 1) {
+              acc = bc_stream_row_smem<1, 0>(srow, l.cols, l.kk, xs, ex, f, lane);
+            } else {
+              acc = bc_stream_row_smem<2, 0>(srow, l.cols, l.kk, xs, ex, f, lane);
+            }
+          }
           if (lane == r) dl = (float)acc;
         }
         if (lane < d.nrows) {
@@ -686,7 +697,7 @@ __global__ void k_bc_selftest(const float* __restrict__ w, float* eps_fast, floa
   if (blockIdx.x == 0 && threadIdx.x == 0) *ok = f.ok;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float x = w[i];
-    eps_fast[i] = bc_qerr<true>(x, f);
+    eps_fast[i] = bc_qerr_own_range(x, f);
     eps_div[i] = __fsub_rn(fake_quant<false>(x, q), x);
   }
 }

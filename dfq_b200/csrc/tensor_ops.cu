@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <mutex>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dfq {
@@ -227,6 +229,99 @@ k_quant(const float* __restrict__ x, float* __restrict__ y, int64_t n, QuantScal
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused activation observer + fake quantization: ONE launch for QuantMeasure.forward (quantize.py:102-119) and for the
+// per-forward weight / bias quantization of the Quant* / Q* layers (quantize.py:24-35,194-203).
+//
+//   phase 1  per-sample min/max of x viewed as [batch, per]: the (sample, split) work items are dealt to the CTAs of a
+//            persistent cooperative grid; every item leaves one (min, max) pair in `scratch` (plain stores, no init)
+//   -------- grid barrier ---------------------------------------------------------------------------------------
+//   phase 2  EVERY CTA reduces the splits and takes the batch mean the same way (float64, sample order: bit-identical
+//            everywhere), derives the running-statistics update and the quantization range from the OLD running values it
+//            read before the barrier; block 0 alone writes the updated running_min / running_max back
+//   phase 3  fake-quantize x -> y with that range (second read of x: an L2 hit for activation-sized tensors)
+//
+// flags: OBS_UPDATE  running = (min(running_min, stat_min), max(running_max, stat_max))        quantize.py:103-107
+//        OBS_EMA     running = running*(1-m) + stat*m (after OBS_UPDATE), range = the batch stat quantize.py:109-113
+//        OBS_OWN     no running buffers: range = the statistic itself (weights: batch 1 = per-tensor min/max)
+//        otherwise   range = the (updated) running values                                        quantize.py:115-119
+enum { OBS_UPDATE = 1, OBS_EMA = 2, OBS_OWN = 4 };
+
+template <bool RECIP>
+__global__ void __launch_bounds__(kThreads)
+k_observe_quant(const float* __restrict__ x, float* __restrict__ y, int64_t batch, int64_t per, int splits,
+                float* running_min, float* running_max, float* __restrict__ scratch, float* stat_out, int flags, float momentum,
+                int num_bits, int symmetric, int prologue) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ float red[2 * kWarps];
+  __shared__ float s_range[2];
+  // the running statistics as they are BEFORE this call (block 0 overwrites them after the barrier)
+  float old_min = 0.f, old_max = 0.f;
+  if (!(flags & OBS_OWN)) { old_min = __ldcg(running_min); old_max = __ldcg(running_max); }
+  const int64_t chunk = (per + splits - 1) / splits;
+  const int64_t items = batch * splits;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t b = it / splits, sp = it - b * splits;
+    const int64_t lo = sp * chunk, hi = min(per, lo + chunk);
+    float mn = DFQ_INF, mx = -DFQ_INF;
+    if (hi > lo) flat_minmax(x + b * per + lo, hi - lo, threadIdx.x, kThreads, mn, mx);
+    __syncthreads();
+    block_minmax(mn, mx, red);
+    if (threadIdx.x == 0) { __stcg(scratch + 2 * it, mn); __stcg(scratch + 2 * it + 1, mx); }
+  }
+  __threadfence();
+  grid.sync();
+  if (threadIdx.x < 32) {
+    // batch mean of the per-sample extrema: float64, sample order, one rounding (as k_batch_mean); lanes over samples
+    double a = 0.0, c = 0.0;
+    for (int64_t b = threadIdx.x; b < batch; b += 32) {
+      float mn = DFQ_INF, mx = -DFQ_INF;
+      for (int sp = 0; sp < splits; ++sp) {
+        mn = fminf(mn, __ldcg(scratch + 2 * (b * splits + sp))); mx = fmaxf(mx, __ldcg(scratch + 2 * (b * splits + sp) + 1));
+      }
+      a += (double)mn; c += (double)mx;
+    }
+    // fixed-shape tree over the 32 lanes: identical in every CTA
+    a = warp_sum(a); c = warp_sum(c);
+    if (threadIdx.x == 0) {
+      const float st_min = (float)(a / (double)batch), st_max = (float)(c / (double)batch);
+      float r_min = old_min, r_max = old_max, q_min, q_max;
+      if (flags & OBS_OWN) { q_min = st_min; q_max = st_max; }
+      else {
+        if (flags & OBS_UPDATE) { r_min = fminf(r_min, st_min); r_max = fmaxf(r_max, st_max); }
+        if (flags & OBS_EMA) {
+          const float om = (float)(1.0 - (double)momentum);
+          r_min = __fadd_rn(__fmul_rn(r_min, om), __fmul_rn(st_min, momentum));
+          r_max = __fadd_rn(__fmul_rn(r_max, om), __fmul_rn(st_max, momentum));
+          q_min = st_min; q_max = st_max;
+        } else { q_min = r_min; q_max = r_max; }
+        if (blockIdx.x == 0) { __stcg(running_min, r_min); __stcg(running_max, r_max); }
+      }
+      if (blockIdx.x == 0 && stat_out) { stat_out[0] = st_min; stat_out[1] = st_max; }
+      s_range[0] = q_min; s_range[1] = q_max;
+    }
+  }
+  __syncthreads();
+  QuantScalars q;
+  if (prologue == 0) q = quant_scalars((double)s_range[0], (double)s_range[1], num_bits, symmetric);
+  else q = quant_scalars_f32(s_range[0], s_range[1], num_bits, symmetric, prologue == 2);
+  const int64_t n = batch * per;
+  const int64_t start = blockIdx.x * (int64_t)kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
+  if (((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = start; i < n4; i += stride) {
+      const float4 v = ldg_stream((const float4*)x + i);
+      float4 r;
+      r.x = fake_quant<RECIP>(v.x, q); r.y = fake_quant<RECIP>(v.y, q); r.z = fake_quant<RECIP>(v.z, q); r.w = fake_quant<RECIP>(v.w, q);
+      stg_stream((float4*)y + i, r);
+    }
+    for (int64_t j = (n4 << 2) + start; j < n; j += stride) y[j] = fake_quant<RECIP>(x[j], q);
+  } else {
+    for (int64_t j = start; j < n; j += stride) y[j] = fake_quant<RECIP>(x[j], q);
+  }
+}
+
 // one warp per row (short rows) or one CTA per row
 __global__ void __launch_bounds__(kThreads)
 k_range_rows(const float* __restrict__ w, int64_t rows, int64_t row_len, float* out_min, float* out_max, int cta_row) {
@@ -401,6 +496,35 @@ extern "C" int dfq_observer_update(float* running_min, float* running_max, const
   DFQ_REQUIRE(running_min && running_max && stat2 && (mode == 1 || mode == 2), "bad argument");
   k_observer_update<<<1, 32, 0, (cudaStream_t)stream>>>(running_min, running_max, stat2, mode, momentum);
   DFQ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+extern "C" int dfq_observe_quant(const float* x, float* y, int64_t batch, int64_t per_sample, float* running_min,
+                                 float* running_max, float* stat_out2, int flags, float momentum, int num_bits, int symmetric,
+                                 int div_mode, int prologue, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DFQ_REQUIRE(x && y && batch > 0 && per_sample > 0, "bad argument");
+  DFQ_REQUIRE((flags & OBS_OWN) || (running_min && running_max), "running statistics required unless OBS_OWN");
+  DFQ_REQUIRE((flags & (OBS_UPDATE | OBS_EMA | OBS_OWN)) != 0, "nothing to observe: use dfq_quant_dequant_dev");
+  DFQ_REQUIRE(num_bits >= 1 && num_bits <= 32 && prologue >= 0 && prologue <= 2, "num_bits / prologue");
+  static int per_sm_recip = 0, per_sm_div = 0;
+  int& per_sm = div_mode ? per_sm_recip : per_sm_div;
+  const void* fn = div_mode ? (const void*)k_observe_quant<true> : (const void*)k_observe_quant<false>;
+  if (per_sm == 0) DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+  if (per_sm < 1) { set_error("k_observe_quant does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
+  const int sms = std::max(1, sm_count());
+  const int64_t n = batch * per_sample;
+  // enough CTAs to fill the machine for big tensors, few for small ones (a grid barrier costs with the grid size)
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * std::min(per_sm, 4), (n + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16)));
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>((per_sample + kThreads * 16 - 1) / (kThreads * 16), std::max<int64_t>(1, grid / batch)));
+  float* scratch = nullptr;
+  DFQ_CUDA(cudaMallocAsync((void**)&scratch, sizeof(float) * 2 * (size_t)batch * splits, st));
+  void* args[] = {(void*)&x, (void*)&y, (void*)&batch, (void*)&per_sample, (void*)&splits, (void*)&running_min, (void*)&running_max,
+                  (void*)&scratch, (void*)&stat_out2, (void*)&flags, (void*)&momentum, (void*)&num_bits, (void*)&symmetric, (void*)&prologue};
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st);
+  cudaFreeAsync(scratch, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(k_observe_quant)");
   return 0;
 }
 

@@ -117,10 +117,11 @@ class Session:
         self._layers.append(dict(w_off=w_off, bias_off=b_off, rows=rows, cols=cols, kk=kk, has_bias=bias is not None))
         return len(self._layers) - 1
 
-    def alloc_layer(self, rows: int, cols: int, kk: int) -> int:
-        """Reserve an (uninitialised, device-only) layer: weight [rows, cols*kk] and bias [rows]."""
+    def alloc_layer(self, rows: int, cols: int, kk: int, bias_off: Optional[int] = None) -> int:
+        """Reserve an (uninitialised, device-only) layer: weight [rows, cols*kk] and bias [rows] (`bias_off`: a range the
+        caller reserved elsewhere, e.g. one block holding the biases of a whole stack)."""
         w_off = self.alloc(rows * cols * kk)
-        b_off = self.alloc(rows)
+        b_off = self.alloc(rows) if bias_off is None else int(bias_off)
         self._layers.append(dict(w_off=w_off, bias_off=b_off, rows=rows, cols=cols, kk=kk, has_bias=False))
         return len(self._layers) - 1
 
@@ -296,7 +297,8 @@ class Session:
             if rel_in[l] > rel_out[l]:
                 raise DfqError("relations must be in forward chain order (as utils.relation.create_relation emits)")
         rt = np.zeros(nR, dtype=_lib.RELATION_DT)
-        s_offs = []
+        # the accumulated scale vectors (Relation.S, the result a multi-GPU step exchanges) sit in ONE contiguous block
+        s_offs = [self.alloc(self._layers[a]["rows"]) for (a, _, _, _) in relations]
         roles: Dict[int, dict] = {}
         for i, (a, b, bnw, bnb) in enumerate(relations):
             la, lb = self._layers[a], self._layers[b]
@@ -308,8 +310,7 @@ class Session:
             r["first"] = a; r["second"] = b; r["channels"] = C1; r["groups"] = G
             r["gi"] = C1 // G; r["go"] = lb["rows"] // G
             r["bn_w_off"] = bnw; r["bn_b_off"] = bnb
-            r["s_acc_off"] = self.alloc(C1); r["s_step_off"] = self.alloc(C1); r["inv_off"] = self.alloc(C1)
-            s_offs.append(int(r["s_acc_off"]))
+            r["s_acc_off"] = s_offs[i]; r["s_step_off"] = self.alloc(C1); r["inv_off"] = self.alloc(C1)
             roles.setdefault(a, {})["rel_out"] = i
             roles[a]["group"] = int(groups[i])
             rb = roles.setdefault(b, {})

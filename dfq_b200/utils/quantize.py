@@ -5,9 +5,10 @@ QConv2d, QuantConv2d, QuantNConv2d, QLinear, QuantLinear, QuantNLinear, set_laye
 arithmetic runs in libdfq_sm100.so:
 
   utils/quantize.py:23-76    UniformQuantize.forward -> dfq_quant_dequant / dfq_quant_dequant_dev
-  utils/quantize.py:102-119  QuantMeasure.forward    -> dfq_act_minmax_per_sample + dfq_observer_update +
-                                                       dfq_quant_dequant_dev (no float() host syncs)
-  utils/quantize.py:176-205  per-forward weight / bias quantization of the Q*/Quant* layers
+  utils/quantize.py:102-119  QuantMeasure.forward    -> dfq_observe_quant: statistic + running update + quantization in
+                                                       ONE launch, no float() host syncs (eval mode without update_stat:
+                                                       dfq_quant_dequant_dev on the device-resident range)
+  utils/quantize.py:176-205  per-forward weight / bias quantization of the Q*/Quant* layers -> dfq_observe_quant (own range)
 
 Numerics.  The reference runs the same Python on CPU tensors (weights during
 calibration) and on CUDA tensors (activations, per-forward weights during inference), and PyTorch's two
@@ -124,6 +125,34 @@ def per_sample_minmax_mean(x, batch=None):
     return out
 
 
+OBS_UPDATE, OBS_EMA, OBS_OWN = 1, 2, 4      # include/dfq_b200.h DFQ_OBS_*
+
+
+def observe_and_quant(x, num_bits, flags, running_min=None, running_max=None, momentum=0.1, batch=None, symmetric=False,
+                      prologue=0, out=None, div_mode=None):
+    """ONE launch: per-sample min/max -> batch mean -> running-statistics update -> fake quantization (dfq_observe_quant).
+    Returns Q(x) on x's device; the running buffers (device tensors) are updated in place on the GPU, nothing syncs."""
+    lib = _lib.load()
+    xd, from_cpu = _dev_f32(x)
+    if div_mode is None:
+        div_mode = 0 if from_cpu else 1
+    if batch is None:
+        batch = xd.shape[0] if xd.dim() > 0 else 1
+    batch = max(1, int(batch))
+    per = xd.numel() // batch
+    yd = out if (out is not None and out.is_cuda and out.is_contiguous()) else torch.empty_like(xd)
+    if xd.numel():
+        _lib.check(lib.dfq_observe_quant(_ptr(xd), _ptr(yd), batch, per,
+                                         _ptr(running_min) if running_min is not None else None,
+                                         _ptr(running_max) if running_max is not None else None, None, int(flags),
+                                         C.c_float(momentum), int(num_bits), 1 if symmetric else 0, int(div_mode), int(prologue),
+                                         _lib.stream_ptr()), "dfq_observe_quant")
+    if out is not None and yd is not out:
+        out.copy_(yd.view(out.shape))
+        return out
+    return yd.view(x.shape).cpu() if from_cpu and out is None else yd.view(x.shape)
+
+
 class UniformQuantize(InplaceFunction):
     """Uniform fake quantization with a straight-through gradient (quantize.py:14-83)."""
 
@@ -137,8 +166,12 @@ class UniformQuantize(InplaceFunction):
         if ctx.inplace:
             ctx.mark_dirty(input)
         out = input if inplace else None
-        if min_value is None or max_value is None:
-            # quantize.py:24-35: y = input.view(B // num_chunks, -1); min = y.min(-1)[0].mean(-1)  (0-d tensors)
+        if min_value is None and max_value is None:
+            # quantize.py:24-35: y = input.view(B // num_chunks, -1); min = y.min(-1)[0].mean(-1)  (0-d tensors) - statistic
+            # and quantization in one launch
+            res = observe_and_quant(input, num_bits, OBS_OWN, batch=max(1, input.shape[0] // num_chunks), symmetric=symmetric,
+                                    prologue=2 if input.is_cuda else 1, out=out)
+        elif min_value is None or max_value is None:
             stat = per_sample_minmax_mean(input, batch=max(1, input.shape[0] // num_chunks))
             mn_t = stat[0:1] if min_value is None else stat.new_full((1,), float(min_value))
             mx_t = stat[1:2] if max_value is None else stat.new_full((1,), float(max_value))
@@ -167,6 +200,30 @@ class _QuantByBuffers(InplaceFunction):
     @staticmethod
     def backward(ctx, grad_output):
         return grad_output, None, None, None
+
+
+class _ObserveQuant(InplaceFunction):
+    """The observer's statistic, running update and fake quantization in one launch (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, input, num_bits, flags, rmin, rmax, momentum):
+        return observe_and_quant(input, num_bits, flags, rmin, rmax, momentum)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None, None, None, None, None
+
+
+class _QuantOwnRange(InplaceFunction):
+    """quantize(w, bits, float(w.min()), float(w.max())) in one launch (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, input, num_bits):
+        return observe_and_quant(input, num_bits, OBS_OWN, batch=1, prologue=0)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None
 
 
 class QuantMeasure(nn.Module):
@@ -202,20 +259,11 @@ class QuantMeasure(nn.Module):
             if from_cpu and staged.device != input.device:
                 return self.forward(staged).to(input.device)
         self._buffers_on(input.device)
-        stat = None
-        if self.update_stat:
-            stat = per_sample_minmax_mean(input)
-            _lib.check(lib.dfq_observer_update(_ptr(self.running_min), _ptr(self.running_max), _ptr(stat), 1,
-                                               C.c_float(self.momentum), _lib.stream_ptr()), "dfq_observer_update")
-        if self.training:
-            if stat is None:
-                stat = per_sample_minmax_mean(input)
-            _lib.check(lib.dfq_observer_update(_ptr(self.running_min), _ptr(self.running_max), _ptr(stat), 2,
-                                               C.c_float(self.momentum), _lib.stream_ptr()), "dfq_observer_update")
-            mn_t, mx_t = stat[0:1], stat[1:2]
-        else:
-            mn_t, mx_t = self.running_min, self.running_max
-        return _QuantByBuffers.apply(input, self.num_bits, mn_t, mx_t)
+        flags = (OBS_UPDATE if self.update_stat else 0) | (OBS_EMA if self.training else 0)
+        if flags:
+            # statistic -> running update (quantize.py:103-113) -> quantization: one stream-ordered launch, no host sync
+            return _ObserveQuant.apply(input, self.num_bits, flags, self.running_min, self.running_max, self.momentum)
+        return _QuantByBuffers.apply(input, self.num_bits, self.running_min, self.running_max)
 
     def set_update_stat(self, update_stat):
         self.update_stat = update_stat
@@ -223,8 +271,7 @@ class QuantMeasure(nn.Module):
 
 def _quant_param_per_forward(w, num_bits):
     """quantize(w, bits, float(w.min()), float(w.max())) (quantize.py:194-196) without the two syncs."""
-    mm = tensor_minmax(w)
-    return _QuantByBuffers.apply(w, num_bits, mm[0:1], mm[1:2])
+    return _QuantOwnRange.apply(w, num_bits)
 
 
 class QConv2d(nn.Conv2d):

@@ -181,7 +181,17 @@ class DeviceStack:
         self.n_layers = 2 * n_blocks
         C, kk = channels, k * k
         self.N = C * C * kk
-        self.layers = [sess.alloc_layer(C, C, kk) for _ in range(self.n_layers)]
+        # arena layout: all weights | all biases | all BN vectors: the small per-channel state (what a multi-GPU step
+        # exchanges) is ONE contiguous window behind the weights
+        w_first = sess.alloc(0)
+        bias_block = None
+        self.layers = []
+        for i in range(self.n_layers):
+            self.layers.append(sess.alloc_layer(C, C, kk, bias_off=-1))
+        bias_block = sess.alloc(self.n_layers * C)
+        for i, li in enumerate(self.layers):
+            sess.layer(li)["bias_off"] = bias_block + i * C
+        self.bias_begin = bias_block
         self.w_begin = sess.layer(self.layers[0])["w_off"]
         # per-layer BN vectors: gamma, beta, mean, var, fake_w, fake_b
         self.vec = [dict((n, sess.alloc(C)) for n in ("gamma", "beta", "mean", "var", "fake_w", "fake_b"))
@@ -232,6 +242,16 @@ class DeviceStack:
     def state(self) -> torch.Tensor:
         """The mutable region (weights, biases, BN vectors) as one flat view - what a step reads and writes."""
         return self.sess.view(self.w_begin, self.state_floats)
+
+    def channel_state(self) -> torch.Tensor:
+        """Everything a calibration step produces besides the weights: corrected biases and the BN vectors
+        (fake_weight / fake_bias after the fold) of every layer, one contiguous window (SURVEY 8(e) "Collective")."""
+        return self.sess.view(self.bias_begin, self.vec_end - self.bias_begin)
+
+    def scale_state(self) -> torch.Tensor:
+        """The accumulated scale vectors Relation.S of every block (relation.py:20-24), one contiguous window."""
+        lo = min(self.cle_plan["s_offs"])
+        return self.sess.view(lo, max(self.cle_plan["s_offs"]) + self.C - lo)
 
     def block_arrays(self, state: torch.Tensor, b: int):
         """Block `b` of a flat state image (state() or a saved copy of it) as host numpy arrays: a list of two dicts

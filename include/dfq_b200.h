@@ -249,6 +249,34 @@ int dfq_act_minmax_per_sample(const float* x, int64_t batch, int64_t per_sample,
 int dfq_observer_update(float* running_min, float* running_max, const float* stat2, int mode, float momentum,
                         void* stream);
 
+/* QuantMeasure.forward in ONE launch (quantize.py:102-119): per-sample min/max -> batch mean -> running
+ * statistics update -> fake quantization of x into y, a persistent cooperative kernel with one grid barrier.  flags:
+ *   DFQ_OBS_UPDATE (1)  update_stat: running = (min(running_min, stat_min), max(running_max, stat_max))  quantize.py:103-107
+ *   DFQ_OBS_EMA    (2)  training: running = running*(1-momentum) + stat*momentum (after the update), and the range used for
+ *                       quantization is the batch statistic                                               quantize.py:109-113
+ *   DFQ_OBS_OWN    (4)  no running buffers (may be NULL): quantize with the statistic itself - with batch = 1 this is
+ *                       quantize(w, bits, float(w.min()), float(w.max())) (quantize.py:194-196) or, with prologue 1/2, the
+ *                       implicit-range path of quantize.py:24-35 used for biases
+ * Without DFQ_OBS_EMA / DFQ_OBS_OWN the range is the updated running pair (quantize.py:115-119).  stat_out2 (optional)
+ * receives the batch statistic.  div_mode / prologue as in dfq_quant_dequant_dev. */
+#define DFQ_OBS_UPDATE 1
+#define DFQ_OBS_EMA 2
+#define DFQ_OBS_OWN 4
+int dfq_observe_quant(const float* x, float* y, int64_t batch, int64_t per_sample, float* running_min, float* running_max,
+                      float* stat_out2, int flags, float momentum, int num_bits, int symmetric, int div_mode, int prologue,
+                      void* stream);
+
+/* BN-statistics matching loss of the distilled-data generation (ZeroQ/distill_data.py:171-196) on one
+ * BatchNorm input x [n, c, hw] (contiguous):  loss2[0] = sum_{n,c} (bn_mean[c] - mean_hw x)^2 / c,
+ * loss2[1] = sum_{n,c} (bn_std[c] - std_hw(x + eps))^2 / c  (unbiased std; own_loss, distill_data.py:41-46).
+ * One pass over x; mean_out / std_out [n*c] are kept for the backward pass. */
+int dfq_bnstat_loss_fwd(const float* x, int64_t n, int64_t c, int64_t hw, const float* bn_mean, const float* bn_std,
+                        float eps, float* mean_out, float* std_out, double* loss2, void* stream);
+/* d(g[0]*loss2[0] + g[1]*loss2[1]) / dx written (accumulate = 0) or added (1) to grad_x; grad_loss2 = device float[2]. */
+int dfq_bnstat_loss_bwd(const float* x, float* grad_x, int64_t n, int64_t c, int64_t hw, const float* bn_mean,
+                        const float* bn_std, float eps, const float* mean_in, const float* std_in,
+                        const float* grad_loss2, int accumulate, void* stream);
+
 /* Per-row extrema of a [rows, row_len] matrix (dfq.py:50,54: range of weight_first_group[ii]). */
 int dfq_range_rows(const float* w, int64_t rows, int64_t row_len, float* out_min, float* out_max,
                    void* stream);

@@ -267,6 +267,28 @@ class FakeLib:
         out[0], out[1] = O.per_sample_minmax_mean(x)
         return 0
 
+    def dfq_observe_quant(self, x_p, y_p, batch, per, rmin_p, rmax_p, stat_p, flags, momentum, bits, sym, div_mode, prologue, stream):
+        self.calls.append("dfq_observe_quant")
+        x = _floats(x_p, batch * per); y = _floats(y_p, batch * per)
+        st_min, st_max = O.per_sample_minmax_mean(x.reshape(batch, per))
+        if flags & 4:
+            q_min, q_max = st_min, st_max
+        else:
+            rmin = _floats(rmin_p, 1); rmax = _floats(rmax_p, 1)
+            if flags & 1:
+                rmin[0] = min(rmin[0], st_min); rmax[0] = max(rmax[0], st_max)
+            if flags & 2:
+                m = f32(_val(momentum)); om = f32(1.0 - float(m))
+                rmin[0] = rmin[0] * om + st_min * m; rmax[0] = rmax[0] * om + st_max * m
+                q_min, q_max = st_min, st_max
+            else:
+                q_min, q_max = rmin[0], rmax[0]
+        if _val(stat_p):
+            st = _floats(stat_p, 2); st[0] = st_min; st[1] = st_max
+        tmp = np.array([q_min, q_max], f32)
+        return self.dfq_quant_dequant_dev(x_p, y_p, batch * per, tmp[0:1].ctypes.data, tmp[1:2].ctypes.data, bits, sym, div_mode,
+                                          prologue, None, stream)
+
     def dfq_observer_update(self, rmin_p, rmax_p, stat_p, mode, momentum, stream):
         rmin = _floats(rmin_p, 1); rmax = _floats(rmax_p, 1); st = _floats(stat_p, 2)
         m = f32(_val(momentum))

@@ -363,3 +363,63 @@ def test_bias_correction_alone_against_reference_produced_numbers(name):
     Gate: 1e-5 normwise."""
     worst = run_bias_correction_against_reference_fixture(name)
     print("bias correction vs reference-produced numbers (%s): worst normwise error %.3g" % (name, worst))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_fused_observer_matches_reference_vectors_and_is_one_launch():
+    """QuantMeasure.forward as ONE launch (dfq_observe_quant): update_stat / training-EMA / eval paths against the vectors
+    the REFERENCE's QuantMeasure produced on the CPU (tests/golden/ref_ops.npz: obs_*, ema_*), plus the own-range modes
+    (per-forward weight quantization, implicit-range bias quantization qimp_*) and a large activation tensor against the
+    oracle; every case is also compared with the separate launches (statistic, update, quantize) bit for bit."""
+    import ctypes as C
+    from dfq_b200 import _lib
+    from dfq_b200.utils import quantize as Q
+    ops = np.load(os.path.join(GOLD, "ref_ops.npz"))
+    # (1) update_stat in eval mode: running range follows the batch statistic, output quantized with the UPDATED range
+    x = torch.from_numpy(ops["obs_in"].copy())
+    qm = Q.QuantMeasure(True).eval()
+    y = qm(x)                                   # CPU input: staged through the GPU, true division like the reference's CPU run
+    assert abs(float(qm.running_min) - float(ops["obs_min"])) <= 1e-6 * abs(float(ops["obs_min"]))
+    assert abs(float(qm.running_max) - float(ops["obs_max"])) <= 1e-6 * abs(float(ops["obs_max"]))
+    want = O.quantize(ops["obs_in"], 8, float(qm.running_min), float(qm.running_max))
+    assert np.array_equal(y.numpy(), want)
+    assert np.abs(y.numpy() - ops["obs_out"]).max() <= 1.001 * (float(ops["obs_max"]) - float(ops["obs_min"])) / 255
+    # (2) training: EMA of the statistic, quantized with the statistic itself
+    qm2 = Q.QuantMeasure(False).train()
+    y2 = qm2(x)
+    assert abs(float(qm2.running_min) - float(ops["ema_min"])) <= 2e-6 * abs(float(ops["ema_min"]))
+    assert abs(float(qm2.running_max) - float(ops["ema_max"])) <= 2e-6 * abs(float(ops["ema_max"]))
+    mn, mx = O.per_sample_minmax_mean(ops["obs_in"].reshape(ops["obs_in"].shape[0], -1))
+    assert np.array_equal(y2.detach().numpy(), O.quantize(ops["obs_in"], 8, float(mn), float(mx)))
+    # (3) implicit-range (bias) path: bit-exact against the reference's vectors
+    b = torch.from_numpy(ops["qimp_in"].copy())
+    assert np.array_equal(Q.quantize(b, num_bits=16).numpy(), ops["qimp_out16"])
+    assert np.array_equal(Q.quantize(b, num_bits=8).numpy(), ops["qimp_out8"])
+    # (4) a large CUDA activation, all three flag combinations, against the separate launches
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xa = torch.randn(64, 64, 56, 56, device="cuda", generator=g) * 1.7          # 12.8 M elements (ResNet-18 conv input)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    for flags in (1, 2, 3):
+        rmin = torch.tensor([-0.5], device="cuda"); rmax = torch.tensor([0.7], device="cuda")
+        fused = Q.observe_and_quant(xa, 8, flags, rmin, rmax, 0.1)
+        smin = torch.tensor([-0.5], device="cuda"); smax = torch.tensor([0.7], device="cuda")
+        stat = Q.per_sample_minmax_mean(xa)
+        if flags & 1:
+            _lib.check(lib.dfq_observer_update(P(smin), P(smax), P(stat), 1, C.c_float(0.1), _lib.stream_ptr()), "upd")
+        if flags & 2:
+            _lib.check(lib.dfq_observer_update(P(smin), P(smax), P(stat), 2, C.c_float(0.1), _lib.stream_ptr()), "ema")
+            sep = Q.fake_quant_device_range(xa, 8, stat[0:1], stat[1:2])
+        else:
+            sep = Q.fake_quant_device_range(xa, 8, smin, smax)
+        assert torch.equal(rmin, smin) and torch.equal(rmax, smax), flags
+        assert torch.equal(fused, sep), (flags, (fused != sep).sum().item())
+    # per-sample statistic itself vs plain torch
+    want_max = xa.view(64, -1).max(-1)[0].double().mean(); want_min = xa.view(64, -1).min(-1)[0].double().mean()
+    rmin = torch.zeros(1, device="cuda"); rmax = torch.zeros(1, device="cuda")
+    Q.observe_and_quant(xa, 8, 1, rmin, rmax, 0.1)
+    assert abs(float(rmax) - float(want_max)) <= 1e-6 * float(want_max) and abs(float(rmin) - float(want_min)) <= 1e-6 * abs(float(want_min))
+    # (5) own range, batch 1: quantize(w, bits, float(w.min()), float(w.max())) on a CUDA weight
+    w = torch.randn(256, 128, 3, 3, device="cuda", generator=g)
+    got = Q._quant_param_per_forward(w, 8)
+    assert torch.equal(got, _eager_q(w, 8, float(w.min()), float(w.max())))
