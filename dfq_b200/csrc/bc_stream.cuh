@@ -44,7 +44,7 @@ constexpr int kBcThreads = (kBcConsumers + 1) * 32;
 constexpr int kBcStages = DFQ_BC_STAGES;
 constexpr int kBcExCols = 512;                // expectation values a consumer warp caches in shared memory (2 KB per warp)
 
-enum { TK_SKIP = 3, TK_END = 4 };
+enum { BTK_SKIP = 3, BTK_END = 4 };
 
 struct BcFastQuant {
   float neg_min, min_v, scale, rcp, qmin, qmax;
@@ -103,10 +103,10 @@ struct BcRing {
   }
   // behind the ring: one expectation cache per consumer warp
   __device__ __forceinline__ float* ex_cache(int warp) const {
-    return (float*)(base + ring_bytes()) + (size_t)warp * kBcExCols;
+    return (float*)(base + ring_bytes()) + (size_t)warp * (kBcExCols + 4);
   }
   __host__ __device__ static constexpr size_t ring_bytes() { return (((size_t)kBcStages * kStageBytes + 16 * kBcStages + 16 + kBcStages * sizeof(TileDesc)) + 127) & ~(size_t)127; }
-  static constexpr size_t smem_bytes() { return ring_bytes() + (size_t)kBcConsumers * kBcExCols * 4 + 64; }
+  static constexpr size_t smem_bytes() { return ring_bytes() + (size_t)kBcConsumers * (kBcExCols + 4) * 4 + 64; }
 };
 
 // Producer lane: put item `d` at sequence number n.
@@ -120,6 +120,17 @@ __device__ __forceinline__ void bc_produce(BcRing& ring, unsigned long long n, c
   } else {
     mbar_arrive(ring.full + s);
   }
+}
+
+// Consumer side: wait for item n; returns its stage.
+__device__ __forceinline__ int bc_take(BcRing& ring, unsigned long long n) {
+  const int s = (int)(n % kBcStages);
+  mbar_wait(ring.full + s, (uint32_t)((n / kBcStages) & 1));
+  return s;
+}
+__device__ __forceinline__ void bc_give_back(BcRing& ring, int s, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(ring.empty + s);
 }
 
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {

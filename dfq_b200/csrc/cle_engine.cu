@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "rowpipe.cuh"
 #include "colscan.cuh"
+#include "bc_stream.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -122,6 +123,15 @@ struct RowCtx {
   int first_sweep;
   int inv_cached;        // 1: inv_in[0 .. cols) of the (single) input group is cached in shared memory
 };
+
+// The column scans are rare in the sweep loop (general middle layers only): kept out of line so that their registers do
+// not count against the hot rescale loop (80-register cap at 3 CTAs/SM; ptxas: 668 B -> 0 B of spills).
+template <bool GLOBAL>
+__device__ __noinline__ void colscan_tile_ool(const float* buf, int tid, int row0, int nrows, int J, int kk, int go, int gi,
+                                             bool single_group, bool own, bool use_smem, float* smin, float* smax, float* dmin,
+                                             float* dmax) {
+  colscan_tile<kThreads, GLOBAL>(buf, tid, row0, nrows, J, kk, go, gi, single_group, own, use_smem, smin, smax, dmin, dmax);
+}
 
 // dfq.py:58-59 + :73.  Returns s; *inv is the factor applied to the columns of the second layer.
 __device__ __forceinline__ float solve_scale(float r1, float r2, const DfqCleParams P, float* inv) {
@@ -425,7 +435,7 @@ __device__ __forceinline__ void cle_tile_smem(const RowCtx& c, const DfqCleParam
 }
 
 // Any row length / alignment: CTA per row, the row is read twice (second read is an L2 hit).
-__device__ __forceinline__ void cle_row_generic(const RowCtx& c, const DfqCleParams P, int o,
+__device__ __noinline__ void cle_row_generic(const RowCtx& c, const DfqCleParams P, int o,
                                                 float* red, int& parity, double& dacc) {
   float* rowp = c.w + (size_t)o * c.row_len;
   const int cbase = c.inv_in ? (o / c.in_go) * c.in_gi : 0;
@@ -593,7 +603,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 //   lane 1  per-channel bookkeeping of tile m (publish_row: S, 1/s, bias, BN vectors, derived column extrema)
 //   lane 2  prefetch of the new tile's column extrema into its mailbox
 // `scan`: the initial column scan -- tiles are only loaded, no mailbox traffic.
-__device__ __forceinline__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
+__device__ __noinline__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
                            unsigned long long& count, const DfqCleParams P, int sweep, CleCtl* ctl, bool tr, bool scan) {
   const int lane = threadIdx.x & 31;
   const unsigned long long count0 = count;
@@ -775,9 +785,9 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
           dmin = arena + l.cmin_off; dmax = arena + l.cmax_off;    // buffer 0
         }
         if (d.kind == TK_DIRECT) {   // a row longer than a stage: straight from global memory
-          colscan_tile<kThreads, true>(d.gptr, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
+          colscan_tile_ool<true>(d.gptr, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
         } else {
-          colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
+          colscan_tile_ool<false>(buf, ctid(), d.row0, d.nrows, J, kk, go, gi, single, own, use_smem, smin, smax, dmin, dmax);
         }
         mbar_arrive(ws.done(sidx));
       }
@@ -888,7 +898,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
             for (int r = 0; r < d.nrows; ++r) cle_row_generic(c, P, d.row0 + r, red, parity, dacc);
             if (rs_li >= 0) {
               cbar();     // the rows are final in global memory (st.cg); read them back with ld.cg
-              colscan_tile<kThreads, true>(d.gptr, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
+              colscan_tile_ool<true>(d.gptr, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
                                            rs_min, rs_max, rsx.dmin, rsx.dmax);
             }
             mbar_arrive(ws.done(sidx));
@@ -897,7 +907,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
             cle_tile_smem(c, P, in_mode, buf, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr);
             if (rs_li >= 0 || d.kind != TK_BULK) cbar();      // every row of the tile is final in the stage
             if (rs_li >= 0)
-              colscan_tile<kThreads, false>(buf, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
+              colscan_tile_ool<false>(buf, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
                                             rs_min, rs_max, rsx.dmin, rsx.dmax);
             if (d.kind == TK_BULK) fence_proxy_async_smem();   // my generic-proxy writes -> visible to the bulk store
             else for (int i = ctid(); i < d.floats; i += kThreads) stg_stream1(d.gptr + i, buf[i]);
@@ -939,6 +949,212 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
     __threadfence();
     grid.sync();
     if (*((volatile int*)&ctl->active[n & 1]) == 0) break;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// k_cle_stack: the equalization of a STACK OF TWO-LAYER CHAINS (BASELINE configs[4]; ResNet basic blocks), streaming
+// variant of k_cle_engine built on the warp-autonomous ring of bc_stream.cuh.
+//
+// k_cle_engine keeps one tile per consumer TEAM: every first-layer row pays a CTA-wide reduction barrier and its
+// bookkeeping goes through the producer warp's mailbox; with 3 stages per CTA only ~one 18 KB load per CTA is in flight
+// while a tile is consumed and another one stored (round 1: 26 % of the warp samples wait for data, first-layer pass
+// 5.2 TB/s, second-layer pass 5.8 TB/s, the fold on the plain pipe 6.3 TB/s).  Here, like k_bc_stream:
+//   * one CTA per SM, 8 consumer WARPS + a producer warp, 11 stages; a warp owns whole tiles: no CTA barrier per tile;
+//   * first-layer rows: two passes over the row in shared memory (min/max, then rescale in place) by the warp alone, the
+//     per-channel bookkeeping of dfq.py:62-70 (publish_row) done lane-parallel - lane r retires row r - instead of by one
+//     producer lane;
+//   * second-layer rows: one in-place pass with the reciprocal scales of the layer's columns cached per warp;
+//   * the rescaled tile leaves with a bulk store issued by the consuming warp; the stage is handed back when that store
+//     has READ it, one tile later (the wait is hidden behind the next tile's work);
+//   * same arithmetic, same exit rule per convergence group (the functions of k_cle_engine are reused): weights, S, biases
+//     and BN vectors are bit-identical to the engine's; the convergence metric is summed in a different order (float64).
+// Eligibility (host, dfq_cle_run): two steps; every layer either `first` only or `second` only (col_mode 0) with its column
+// extrema ready (the fold's scan); ungrouped relations; rows that the TMA unit can move (multiple of 4 floats, <= a stage);
+// at most kBcExCols input columns, 3x3 or 1x1 taps; not apply_only.  Everything else runs on k_cle_engine.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Producer lane: this CTA's tiles of one step (layers of converged groups skipped), SKIP padding, one END per consumer.
+__device__ __noinline__ void cle_stack_feed(BcRing& ring, unsigned long long& n, float* arena, PassIter it) {
+  TileDesc d;
+  fence_proxy_async_all();          // rows written before the last grid barrier (bulk + plain stores) -> bulk loads
+  while (it.valid()) { it.fill(d, arena); bc_produce(ring, n++, d); it.next(); }
+  d.gptr = nullptr; d.task = -1; d.row0 = d.nrows = d.floats = 0;
+  d.kind = BTK_SKIP;
+  while (n % kBcConsumers) bc_produce(ring, n++, d);
+  d.kind = BTK_END;
+  for (int i = 0; i < kBcConsumers; ++i) bc_produce(ring, n++, d);
+}
+
+__global__ void __launch_bounds__(kBcThreads, 1)
+k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelation* __restrict__ R, int nR,
+            const int* __restrict__ step_ptr, const int* __restrict__ step_layers, const long long* __restrict__ pass_ptr,
+            DfqCleParams P, CleCtl* ctl, GroupState* G, int nG) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  __shared__ RowCtx wctx[kBcConsumers];
+  BcRing ring;
+  ring.init(ring_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer = (warp == kBcConsumers);
+  unsigned long long n = producer ? 0 : (unsigned long long)warp;
+  for (int g = blockIdx.x * kBcThreads + threadIdx.x; g < nG; g += gridDim.x * kBcThreads) G[g].diff = 10.0;   // dfq.py:81
+  __threadfence();
+  grid.sync();
+
+  for (int sweep = 0;; ++sweep) {
+    const int slot = sweep % 3;
+    for (int p = 0; p < 2; ++p) {
+      if (producer) {
+        if (lane == 0) {
+          PassIter it;
+          it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
+          cle_stack_feed(ring, n, arena, it);
+        }
+      } else {
+        RowCtx& c = wctx[warp];
+        float* inv_s = ring.ex_cache(warp);            // reciprocal scales of the current second layer's columns (+ sentinel)
+        int cur_li = -1, cur_g = -1, pending = -1, kk = 1;
+        double dacc = 0.0;
+        auto flush_metric = [&]() {
+          if (cur_g >= 0) {
+            const double t = warp_sum(dacc);
+            if (lane == 0 && t != 0.0) atomicAdd(&G[cur_g].acc[slot], t);
+          }
+          dacc = 0.0;
+        };
+        auto release_pending = [&]() {                  // the previous tile's bulk store has read its stage: hand it back
+          if (pending >= 0) {
+            if (lane == 0) { bulk_wait_read<0>(); mbar_arrive(ring.empty + pending); }
+            pending = -1;
+          }
+        };
+        for (;; n += kBcConsumers) {
+          const int s = bc_take(ring, n);
+          const TileDesc d = ring.desc[s];
+          if (d.kind == BTK_END || d.kind == BTK_SKIP) {
+            release_pending();
+            bc_give_back(ring, s, lane);
+            if (d.kind == BTK_END) { n += kBcConsumers; break; }
+            continue;
+          }
+          if (d.task != cur_li) {
+            cur_li = d.task;
+            const int g = L[cur_li].group;
+            if (g != cur_g) { flush_metric(); cur_g = g; }
+            __syncwarp();
+            if (lane == 0) make_ctx(c, arena, L, R, cur_li, sweep);
+            __syncwarp();
+            kk = c.kk;
+            if (c.inv_in) {
+              for (int j = lane; j < c.cols; j += 32) inv_s[j] = __ldcg(c.inv_in + j);
+              if (lane == 0) inv_s[c.cols] = 1.f;
+              __syncwarp();
+            }
+          }
+          const int row_len = c.row_len, n4 = row_len >> 2;
+          const uint32_t sbase = smem_u32(ring.stage(s));
+          const double inv_n = c.inv_n;
+          if (c.has_out) {
+            // ---- first layer of a chain: per-row range -> s -> rescale (dfq.py:48-73) --------------------------------
+            RowIn mine; mine.cmn = mine.cmx = 0.f; mine.u = 1.f; mine.s_given = 1.f;
+            if (lane < d.nrows) mine = fetch_row_in(c, P, d.row0 + lane, false);     // this lane's row: column extrema of the pair
+            float ks = 1.f, kinv = 1.f;
+            for (int r = 0; r < d.nrows; ++r) {
+              const uint32_t a0 = sbase + (uint32_t)r * (uint32_t)row_len * 4u;
+              float mn = DFQ_INF, mx = -DFQ_INF;
+#pragma unroll 4
+              for (int i4 = lane; i4 < n4; i4 += 32) {
+                const float4 t = lds_f4(a0 + 16u * i4);
+                mn = fminf(mn, fminf(fminf(t.x, t.y), fminf(t.z, t.w)));
+                mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+              }
+              mn = warp_min(mn); mx = warp_max(mx);
+              RowIn in;
+              in.cmn = __shfl_sync(0xffffffffu, mine.cmn, r); in.cmx = __shfl_sync(0xffffffffu, mine.cmx, r);
+              in.u = 1.f; in.s_given = 1.f;
+              float iv;
+              const float sv = solve_row(P, in, mn, mx, &iv);
+              if (lane == r) { ks = sv; kinv = iv; }
+              if (r == 0) release_pending();            // by now the previous tile's store has long been read
+              float dsum = 0.f;
+#pragma unroll 4
+              for (int i4 = lane; i4 < n4; i4 += 32) {
+                const float4 v = lds_f4(a0 + 16u * i4);
+                float4 t;
+                t.x = __fmul_rn(v.x, sv); t.y = __fmul_rn(v.y, sv); t.z = __fmul_rn(v.z, sv); t.w = __fmul_rn(v.w, sv);
+                sts_f4(a0 + 16u * i4, t);
+                dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
+              }
+              dacc += (double)dsum * inv_n;
+            }
+            if (lane < d.nrows) publish_row(c, P, d.row0 + lane, ks, kinv, mine.cmn, mine.cmx);
+          } else {
+            // ---- second layer: columns scaled by 1/s of the relation (dfq.py:73) ------------------------------------
+            release_pending();
+            for (int r = 0; r < d.nrows; ++r) {
+              const uint32_t a0 = sbase + (uint32_t)r * (uint32_t)row_len * 4u;
+              float dsum = 0.f;
+              if (kk == 9) {
+#pragma unroll 4
+                for (int i4 = lane; i4 < n4; i4 += 32) {
+                  const float4 v = lds_f4(a0 + 16u * i4);
+                  const float4 t = in_scale4<IN_KK9>(v, i4 * 4, inv_s, 1.f, 9);
+                  sts_f4(a0 + 16u * i4, t);
+                  dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
+                }
+              } else {
+#pragma unroll 4
+                for (int i4 = lane; i4 < n4; i4 += 32) {
+                  const float4 v = lds_f4(a0 + 16u * i4);
+                  const float4 t = in_scale4<IN_KK1>(v, i4 * 4, inv_s, 1.f, 1);
+                  sts_f4(a0 + 16u * i4, t);
+                  dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
+                }
+              }
+              dacc += (double)dsum * inv_n;
+            }
+          }
+          // the rescaled tile: generic-proxy writes -> visible to the bulk store, issued by this warp
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { bulk_s2g(d.gptr, ring.stage(s), (uint32_t)d.floats * 4u); bulk_commit(); }
+          pending = s;
+        }
+        flush_metric();
+        if (lane == 0) { bulk_wait_all(); fence_proxy_async_all(); }
+        __threadfence();             // the lanes' bookkeeping stores, before the grid barrier
+      }
+      grid.sync();
+    }
+    // ---- exit rule of dfq.py:105-115, one thread per group (as in k_cle_engine) ---------------------------------------
+    const int nsw = sweep + 1;
+    for (int g = blockIdx.x * kBcThreads + threadIdx.x; g < nG; g += gridDim.x * kBcThreads) {
+      GroupState& st = G[g];
+      if (st.done) continue;
+      const double diff_tmp = st.acc[slot];
+      st.acc[(slot + 2) % 3] = 0.0;
+      if (fabs(st.diff - diff_tmp) > 1e-9) { st.count = 0; st.diff = diff_tmp; }
+      else st.count++;
+      if (g == 0 && sweep < 64) ctl->diffs[sweep] = diff_tmp;
+      const bool cont = (st.diff > P.converge_thres) && (st.count < P.converge_count);
+      const int cap = P.max_sweeps > 0 ? P.max_sweeps : 4096;
+      if (!cont || nsw >= cap) { st.n_sweeps = nsw; st.converged = !cont; st.done = 1; }
+      else atomicAdd(&ctl->active[nsw & 1], 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->active[sweep & 1] = 0;
+    __threadfence();
+    grid.sync();
+    if (*((volatile int*)&ctl->active[nsw & 1]) == 0) break;
   }
 }
 
@@ -1002,6 +1218,73 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
       t += pass_tiles(l);
     }
     max_tiles = std::max(max_tiles, t);
+  }
+
+  // ---- streaming variant for stacks of two-layer chains (k_cle_stack) ----------------------------------------------
+  bool stack_ok = (n_steps == 2) && !params->apply_only;
+  for (int i = 0; stack_ok && i < n_rels; ++i) stack_ok = rels[i].groups == 1;
+  int64_t stack_tiles = 0;
+  for (int p = 0; stack_ok && p < n_steps; ++p)
+    for (int q = step_ptr[p]; stack_ok && q < step_ptr[p + 1]; ++q) {
+      const DfqLayer& l = layers[step_layers[q]];
+      const int row_len = l.cols * l.kk;
+      stack_ok = (row_len % 4 == 0) && row_len <= kStageFloats && (l.w_off % 4 == 0) && (l.kk == 9 || l.kk == 1);
+      if (p == 0) stack_ok = stack_ok && l.rel_in < 0 && l.rel_out >= 0;
+      else stack_ok = stack_ok && l.rel_in >= 0 && l.rel_out < 0 && l.col_mode == 0 && (l.flags & DFQ_LAYER_COLS_READY) &&
+                      l.cols <= kBcExCols;
+      stack_tiles += pass_tiles(l);
+    }
+  {
+    int sms_ = 0, dev_ = 0;
+    DFQ_CUDA(cudaGetDevice(&dev_));
+    DFQ_CUDA(cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_));
+    const bool eligible = stack_ok;
+    stack_ok = eligible && stack_tiles >= (int64_t)64 * sms_;                       // large phases only: small models are latency-bound
+    if (const char* e = getenv("DFQ_CLE_STACK")) stack_ok = eligible && atoi(e) != 0;   // 0: never, 1: whenever eligible (tests)
+    if (stack_ok) {
+      const size_t dyn_s = BcRing::smem_bytes();
+      DFQ_CUDA(cudaFuncSetAttribute(k_cle_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_s));
+      int per_sm_s = 0;
+      DFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_cle_stack, kBcThreads, dyn_s));
+      if (per_sm_s < 1) { set_error("k_cle_stack does not fit on an SM"); return DFQ_E_NOT_COOPERATIVE; }
+      const int grid_s = (int)std::min<int64_t>((int64_t)sms_ * per_sm_s, std::max<int64_t>(1, max_tiles));
+      const int n_entries_s = step_ptr[n_steps];
+      std::vector<long long> pass_ptr_s(n_entries_s + 1, 0);
+      for (int q = 0; q < n_entries_s; ++q) pass_ptr_s[q + 1] = pass_ptr_s[q] + pass_tiles(layers[step_layers[q]]);
+      TablePack tp;
+      const int iL = tp.add(layers, n_layers), iR = tp.add(rels, n_rels), iSP = tp.add(step_ptr, n_steps + 1);
+      const int iSL = tp.add(step_layers, n_entries_s), iPP = tp.add(pass_ptr_s.data(), n_entries_s + 1);
+      int rc;
+      if ((rc = tp.upload(st))) return rc;
+      DfqLayer* dL = tp.ptr<DfqLayer>(iL); DfqRelation* dR = tp.ptr<DfqRelation>(iR);
+      int32_t *dSP = tp.ptr<int32_t>(iSP), *dSL = tp.ptr<int32_t>(iSL);
+      long long* dPP = tp.ptr<long long>(iPP);
+      CleCtl* dctl = nullptr; GroupState* dG = nullptr;
+      DFQ_CUDA(cudaMallocAsync((void**)&dctl, sizeof(CleCtl), st));
+      DFQ_CUDA(cudaMemsetAsync(dctl, 0, sizeof(CleCtl), st));
+      DFQ_CUDA(cudaMallocAsync((void**)&dG, sizeof(GroupState) * n_groups, st));
+      DFQ_CUDA(cudaMemsetAsync(dG, 0, sizeof(GroupState) * n_groups, st));
+      DfqCleParams Pk = *params;
+      void* args[] = {&arena, &dL, (void*)&n_layers, &dR, (void*)&n_rels, &dSP, &dSL, &dPP, &Pk, &dctl, &dG, (void*)&n_groups};
+      DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_stack, dim3(grid_s), dim3(kBcThreads), args, dyn_s, st));
+      CleCtl h;
+      std::vector<GroupState> hg(n_groups);
+      DFQ_CUDA(cudaMemcpyAsync(&h, dctl, sizeof(CleCtl), cudaMemcpyDeviceToHost, st));
+      DFQ_CUDA(cudaMemcpyAsync(hg.data(), dG, sizeof(GroupState) * n_groups, cudaMemcpyDeviceToHost, st));
+      tp.release(st);
+      free_async(dctl, st); free_async(dG, st);
+      DFQ_CUDA(cudaStreamSynchronize(st));
+      result->n_sweeps = 0; result->converged = 1;
+      for (int g = 0; g < n_groups; ++g) {
+        result->n_sweeps = std::max(result->n_sweeps, hg[g].n_sweeps);
+        result->converged &= hg[g].converged;
+        if (group_sweeps) group_sweeps[g] = hg[g].n_sweeps;
+      }
+      result->last_diff = hg[0].diff;
+      memcpy(result->diffs, h.diffs, sizeof(h.diffs));
+      if (trace) fprintf(stderr, "[dfq_cle_run] stack variant: grid %d, sweeps %d, host ms %.3f\n", grid_s, result->n_sweeps, ms_since(h0));
+      return 0;
+    }
   }
 
   h_valid = ms_since(h0);

@@ -515,21 +515,10 @@ __device__ __forceinline__ void bc_feed(BcRing& ring, unsigned long long& n, con
   it.start(ptr, q_begin, q_end, geo);
   while (it.valid()) { it.fill(d); bc_produce(ring, n++, d); it.next(); }
   d.gptr = nullptr; d.task = -1; d.row0 = d.nrows = d.floats = 0;
-  d.kind = TK_SKIP;
+  d.kind = BTK_SKIP;
   while (n % kBcConsumers) bc_produce(ring, n++, d);
-  d.kind = TK_END;
+  d.kind = BTK_END;
   for (int i = 0; i < kBcConsumers; ++i) bc_produce(ring, n++, d);
-}
-
-// Consumer side: wait for item n; returns its stage.
-__device__ __forceinline__ int bc_take(BcRing& ring, unsigned long long n) {
-  const int s = (int)(n % kBcStages);
-  mbar_wait(ring.full + s, (uint32_t)((n / kBcStages) & 1));
-  return s;
-}
-__device__ __forceinline__ void bc_give_back(BcRing& ring, int s, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_arrive(ring.empty + s);
 }
 
 __global__ void __launch_bounds__(kBcThreads, 1)
@@ -569,8 +558,8 @@ k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
       for (;; n += kBcConsumers) {
         const int s = bc_take(ring, n);
         const TileDesc d = ring.desc[s];
-        if (d.kind == TK_END) { bc_give_back(ring, s, lane); n += kBcConsumers; break; }
-        if (d.kind != TK_SKIP) {
+        if (d.kind == BTK_END) { bc_give_back(ring, s, lane); n += kBcConsumers; break; }
+        if (d.kind != BTK_SKIP) {
           float mn = DFQ_INF, mx = -DFQ_INF;
           if (d.kind == TK_BULK && (d.floats & 3) == 0) {
             const float4* b4 = (const float4*)ring.stage(s);
@@ -622,8 +611,8 @@ k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
       for (;; n += kBcConsumers) {
         const int s = bc_take(ring, n);
         const TileDesc d = ring.desc[s];
-        if (d.kind == TK_END) { bc_give_back(ring, s, lane); n += kBcConsumers; break; }
-        if (d.kind == TK_SKIP) { bc_give_back(ring, s, lane); continue; }
+        if (d.kind == BTK_END) { bc_give_back(ring, s, lane); n += kBcConsumers; break; }
+        if (d.kind == BTK_SKIP) { bc_give_back(ring, s, lane); continue; }
         if (d.task != cur) {
           cur = d.task; cur_group = -1;
           b = B[cur]; l = L[b.layer];

@@ -257,8 +257,9 @@ def main():
     out = snapshot(_State.top)
     n_out = max(len(o) for o in _State.outputs)
     for k in range(n_out):
-        out["output_%d" % k] = np.concatenate([o[k].reshape(o[k].shape[0], -1) if o[k].ndim > 1 else o[k].reshape(1, -1)
-                                                 for o in _State.outputs if len(o) > k], axis=0)
+        parts = [o[k].reshape(o[k].shape[0], -1) if o[k].ndim > 1 else o[k].reshape(1, -1) for o in _State.outputs if len(o) > k]
+        width = max(set(p.shape[1] for p in parts), key=lambda w: sum(1 for p in parts if p.shape[1] == w))
+        out["output_%d" % k] = np.concatenate([p for p in parts if p.shape[1] == width], axis=0)
     out["meta"] = np.array(repr(dict(impl=args.impl, which=args.which, flags=flags, gpu=have_gpu, tail_error=err,
                                      library_calls=sorted(set(fake.calls)) if fake is not None else None)))
     np.savez_compressed(args.out, **out)

@@ -298,7 +298,34 @@ def test_large_stack_properties():
     assert torch.allclose(sess.view(st.w_begin, 2 * N), before, rtol=1e-6, atol=0)
 
 
-def test_config5_blocks_match_the_oracle():
+@pytest.mark.parametrize("variant", ["engine", "stack"])
+def test_config5_blocks_match_the_oracle(variant, monkeypatch):
+    monkeypatch.setenv("DFQ_CLE_STACK", "1" if variant == "stack" else "0")
+    _config5_blocks()
+
+
+@pytest.mark.parametrize("channels,k", [(64, 3), (128, 1), (96, 3)])
+def test_stack_kernel_equals_engine_on_other_block_shapes(channels, k, monkeypatch):
+    """k_cle_stack (streaming variant for stacks of two-layer chains) against k_cle_engine on the same bits: several rows per
+    tile (576- and 864-float rows), pointwise blocks (128-float rows, 32 rows per tile), 5 blocks = 5 convergence groups -
+    weights, biases, BN vectors, S and the per-group sweep counts must be bit-identical."""
+    from dfq_b200.engine import Session
+    from dfq_b200.workload import DeviceStack
+    outs = []
+    for variant in ("0", "1"):
+        monkeypatch.setenv("DFQ_CLE_STACK", variant)
+        sess = Session()
+        st = DeviceStack(sess, 5, channels, k, seed=11)
+        st.generate()
+        sess.run_bn_fold(st.fold_plan)
+        res = sess.run_cle_plan(st.cle_plan, cols_ready=st.fold_plan["scanned"])
+        outs.append((st.state().clone(), st.scale_state().clone(), res.group_sweeps.copy(), res.n_sweeps, res.converged))
+    assert outs[0][3] == outs[1][3] and outs[0][4] and outs[1][4] and np.array_equal(outs[0][2], outs[1][2]), (outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][0], outs[1][0]), "weights / biases / BN vectors differ between the two kernels"
+    assert torch.equal(outs[0][1], outs[1][1]), "S differs"
+
+
+def _config5_blocks():
     """The headline workload shape itself (BASELINE configs[4]): Conv[512,512,3,3]+BN+ReLU -> Conv[512,512,3,3]+BN blocks
     through the fused step bench.py times (fold with column scan -> equalization -> correction with range hints) vs the
     oracle on the same bits: weights / first bias / BN vectors bit-exact, corrected bias within 1e-5, 2 sweeps."""

@@ -301,3 +301,56 @@ def test_golden_ncnn_table_through_the_cuda_library(monkeypatch):
     ew, ea = np.abs(got_w / gold_w - 1).max(), np.abs(got_a / gold_a - 1).max()
     print("golden table through CUDA: weight rows %.3g, activation rows %.3g (max relative error)" % (ew, ea))
     assert ew < 1e-5 and ea < 1e-5, (ew, ea)
+
+
+def export_round_trip(tmp_path, monkeypatch=None):
+    """Shared with the CPU twin (tests/test_host_logic.py): calibrate a ResNet-18-shaped graph of QuantN layers, write the
+    ncnn calibration table and the calibration state (export.py), read both back."""
+    from dfq_b200 import dfq, export
+    from dfq_b200.utils import layer_transform as LT
+    from dfq_b200.utils import quantize as Q
+    from dfq_b200.utils.relation import create_relation
+    topo = workload.load_topology(os.path.join(GOLD, "topology_resnet18.json"))
+    graph, bottoms, _ = workload.build_graph(topo, seed=9, conv_cls=Q.QuantNConv2d, linear_cls=Q.QuantNLinear)
+    targ = [Q.QuantNConv2d, Q.QuantNLinear]
+    LT.merge_batchnorm(None, graph, bottoms, targ)
+    rels = create_relation(graph, bottoms, targ)
+    dfq.cross_layer_equalization(graph, rels, targ)
+    dfq.bias_correction(graph, bottoms, targ)
+    g = torch.Generator().manual_seed(1)
+    layers = [m for m in graph.values() if type(m) in targ]
+    for m in layers:                                       # observer ranges as set_quant_minmax / update_quant_range leave them
+        m.quant.running_min.fill_(-float(torch.rand(1, generator=g)) - 0.1); m.quant.running_max.fill_(float(torch.rand(1, generator=g)) + 0.1)
+    table = str(tmp_path / "model.table")
+    names = ["conv_%d" % i for i in range(len(layers))]
+    rows = export.write_ncnn_table(graph, table, targ, names)
+    lines = [l.split() for l in open(table).read().strip().splitlines()]
+    assert len(lines) == 2 * len(layers)
+    for i, m in enumerate(layers):
+        w = m.weight.detach()
+        want_w = 128. / float(w.abs().max())
+        assert lines[i][0] == names[i] + "_param_0" and len(lines[i]) == 1 + w.shape[0]          # one value per output channel
+        assert all(abs(float(v) / want_w - 1) < 1e-6 for v in lines[i][1:]) and abs(rows[i][0] / want_w - 1) < 1e-6
+        want_a = 128. / max(abs(float(m.quant.running_min)), abs(float(m.quant.running_max)))
+        assert lines[len(layers) + i][0] == names[i] and abs(float(lines[len(layers) + i][1]) / want_a - 1) < 1e-6
+    state_path = str(tmp_path / "calibration.pt")
+    export.save_calibration(graph, rels, state_path)
+    state = torch.load(state_path)
+    keys = list(graph.keys())
+    assert len(state["S"]) == len(rels) and all(torch.equal(a, r.S.cpu()) for a, r in zip(state["S"], rels))
+    n_l = n_b = 0
+    for i, k in enumerate(keys):
+        m = graph[k]
+        if type(m) in targ:
+            assert torch.equal(state["layers"][i]["weight"], m.weight.detach().cpu()) and torch.equal(state["layers"][i]["bias"], m.bias.detach().cpu())
+            n_l += 1
+        elif hasattr(m, "fake_bias") and not isinstance(m, str):
+            assert torch.equal(state["bn"][i]["fake_bias"], m.fake_bias.cpu()) and torch.equal(state["bn"][i]["fake_weight"], m.fake_weight.cpu())
+            n_b += 1
+    assert n_l == len(layers) == 21 and n_b == 20
+    return len(lines)
+
+
+def test_export_round_trip_on_cuda_results(tmp_path):
+    """write_ncnn_table / save_calibration on a model calibrated by libdfq_sm100.so (convert_ncnn.py:178-201 format)."""
+    assert export_round_trip(tmp_path) == 42

@@ -286,3 +286,10 @@ def test_bias_correction_alone_against_reference_produced_numbers_cpu(name, monk
     fakelib.install(monkeypatch)
     worst = T.run_bias_correction_against_reference_fixture(name)
     assert worst < 1e-5
+
+
+def test_export_round_trip_cpu(tmp_path, monkeypatch):
+    """CPU twin of tests/test_gpu_pipeline.py::test_export_round_trip_on_cuda_results (oracle-backed executor)."""
+    import test_gpu_pipeline as T
+    fakelib.install(monkeypatch)
+    assert T.export_round_trip(tmp_path) == 42

@@ -136,8 +136,9 @@ def test_patched_ops_agree_with_the_reference_implementation(monkeypatch):
         theirs, seen, _ = _run_patched(ref.layer_transform, ref.quantize.QuantMeasure, model, x)
     finally:
         sys.path[:] = saved_path
-        for k in list(sys.modules):
-            if k not in saved_mods:
+        for k in list(sys.modules):     # forget what was imported from the reference tree (not torch's lazy imports)
+            f = getattr(sys.modules[k], "__file__", None) or ""
+            if k not in saved_mods and f.startswith(refenv.REF_ROOT):
                 del sys.modules[k]
         sys.modules.update(saved_mods)
     assert [i for i, _ in seen] == list(range(N_OBS))
