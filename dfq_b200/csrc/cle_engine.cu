@@ -961,19 +961,28 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
 // bookkeeping goes through the producer warp's mailbox; with 3 stages per CTA only ~one 18 KB load per CTA is in flight
 // while a tile is consumed and another one stored (round 1: 26 % of the warp samples wait for data, first-layer pass
 // 5.2 TB/s, second-layer pass 5.8 TB/s, the fold on the plain pipe 6.3 TB/s).  Here, like k_bc_stream:
-//   * one CTA per SM, 8 consumer WARPS + a producer warp, 11 stages; a warp owns whole tiles: no CTA barrier per tile;
+//   * one CTA per SM, kStackConsumers consumer WARPS + a producer warp, 11 stages; a warp owns whole tiles: no CTA barrier per tile;
 //   * first-layer rows: two passes over the row in shared memory (min/max, then rescale in place) by the warp alone, the
 //     per-channel bookkeeping of dfq.py:62-70 (publish_row) done lane-parallel - lane r retires row r - instead of by one
 //     producer lane;
 //   * second-layer rows: one in-place pass with the reciprocal scales of the layer's columns cached per warp;
-//   * the rescaled tile leaves with a bulk store issued by the consuming warp; the stage is handed back when that store
-//     has READ it, one tile later (the wait is hidden behind the next tile's work);
+//   * the rescaled tile leaves with a bulk store issued by the consuming warp; the stage is handed back as soon as that store
+//     has READ it;
 //   * same arithmetic, same exit rule per convergence group (the functions of k_cle_engine are reused): weights, S, biases
 //     and BN vectors are bit-identical to the engine's; the convergence metric is summed in a different order (float64).
 // Eligibility (host, dfq_cle_run): two steps; every layer either `first` only or `second` only (col_mode 0) with its column
 // extrema ready (the fold's scan); ungrouped relations; rows that the TMA unit can move (multiple of 4 floats, <= a stage);
 // at most kBcExCols input columns, 3x3 or 1x1 taps; not apply_only.  Everything else runs on k_cle_engine.
 // ------------------------------------------------------------------------------------------------------------
+// Consumer warps of k_cle_stack (of the kBcConsumers the CTA has): the pass is far from issue-bound (ncu, 7 consumers: issue
+// slots 19 % busy, 45 % of the warp samples waiting for data) - what matters is how many of the 11 stages are LOADING, i.e.
+// not held by a consumer.  Sequence numbers are dealt modulo this count; the other warps only join the grid barriers.
+#ifndef DFQ_STACK_CONSUMERS
+#define DFQ_STACK_CONSUMERS 4
+#endif
+constexpr int kStackConsumers = DFQ_STACK_CONSUMERS;
+static_assert(kStackConsumers >= 1 && kStackConsumers <= kBcConsumers, "k_cle_stack consumer count");
+
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -990,9 +999,9 @@ __device__ __noinline__ void cle_stack_feed(BcRing& ring, unsigned long long& n,
   while (it.valid()) { it.fill(d, arena); bc_produce(ring, n++, d); it.next(); }
   d.gptr = nullptr; d.task = -1; d.row0 = d.nrows = d.floats = 0;
   d.kind = BTK_SKIP;
-  while (n % kBcConsumers) bc_produce(ring, n++, d);
+  while (n % kStackConsumers) bc_produce(ring, n++, d);
   d.kind = BTK_END;
-  for (int i = 0; i < kBcConsumers; ++i) bc_produce(ring, n++, d);
+  for (int i = 0; i < kStackConsumers; ++i) bc_produce(ring, n++, d);
 }
 
 __global__ void __launch_bounds__(kBcThreads, 1)
@@ -1006,7 +1015,7 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
   ring.init(ring_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool producer = (warp == kBcConsumers);
-  unsigned long long n = producer ? 0 : (unsigned long long)warp;
+  unsigned long long n = producer ? 0 : (unsigned long long)warp;       // (warps >= kStackConsumers never use it)
   for (int g = blockIdx.x * kBcThreads + threadIdx.x; g < nG; g += gridDim.x * kBcThreads) G[g].diff = 10.0;   // dfq.py:81
   __threadfence();
   grid.sync();
@@ -1020,10 +1029,10 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
           it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
           cle_stack_feed(ring, n, arena, it);
         }
-      } else {
+      } else if (warp < kStackConsumers) {
         RowCtx& c = wctx[warp];
         float* inv_s = ring.ex_cache(warp);            // reciprocal scales of the current second layer's columns (+ sentinel)
-        int cur_li = -1, cur_g = -1, pending = -1, kk = 1;
+        int cur_li = -1, cur_g = -1, kk = 1;
         double dacc = 0.0;
         auto flush_metric = [&]() {
           if (cur_g >= 0) {
@@ -1032,19 +1041,12 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
           }
           dacc = 0.0;
         };
-        auto release_pending = [&]() {                  // the previous tile's bulk store has read its stage: hand it back
-          if (pending >= 0) {
-            if (lane == 0) { bulk_wait_read<0>(); mbar_arrive(ring.empty + pending); }
-            pending = -1;
-          }
-        };
-        for (;; n += kBcConsumers) {
+        for (;; n += kStackConsumers) {
           const int s = bc_take(ring, n);
           const TileDesc d = ring.desc[s];
           if (d.kind == BTK_END || d.kind == BTK_SKIP) {
-            release_pending();
             bc_give_back(ring, s, lane);
-            if (d.kind == BTK_END) { n += kBcConsumers; break; }
+            if (d.kind == BTK_END) { n += kStackConsumers; break; }
             continue;
           }
           if (d.task != cur_li) {
@@ -1085,7 +1087,6 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
               float iv;
               const float sv = solve_row(P, in, mn, mx, &iv);
               if (lane == r) { ks = sv; kinv = iv; }
-              if (r == 0) release_pending();            // by now the previous tile's store has long been read
               float dsum = 0.f;
 #pragma unroll 4
               for (int i4 = lane; i4 < n4; i4 += 32) {
@@ -1100,7 +1101,6 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
             if (lane < d.nrows) publish_row(c, P, d.row0 + lane, ks, kinv, mine.cmn, mine.cmx);
           } else {
             // ---- second layer: columns scaled by 1/s of the relation (dfq.py:73) ------------------------------------
-            release_pending();
             for (int r = 0; r < d.nrows; ++r) {
               const uint32_t a0 = sbase + (uint32_t)r * (uint32_t)row_len * 4u;
               float dsum = 0.f;
@@ -1127,8 +1127,15 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
           // the rescaled tile: generic-proxy writes -> visible to the bulk store, issued by this warp
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) { bulk_s2g(d.gptr, ring.stage(s), (uint32_t)d.floats * 4u); bulk_commit(); }
-          pending = s;
+          // ... and the stage goes back to the producer as soon as the store has READ it (~0.1 us for 18 KB; the store itself
+          // completes in the background).  Holding it until the next tile instead (tried first) left every consumer with two
+          // stages and the ring with almost nothing loading.
+          if (lane == 0) {
+            bulk_s2g(d.gptr, ring.stage(s), (uint32_t)d.floats * 4u);
+            bulk_commit();
+            bulk_wait_read<0>();
+            mbar_arrive(ring.empty + s);
+          }
         }
         flush_metric();
         if (lane == 0) { bulk_wait_all(); fence_proxy_async_all(); }

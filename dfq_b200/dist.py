@@ -33,6 +33,17 @@ import torch.nn as nn
 from .engine import Session
 
 
+def _all_gather_flat(recv: torch.Tensor, send: torch.Tensor, group=None):
+    """all_gather_into_tensor; gloo has no CUDA all-gather, so with that backend (the single-GPU multi-process tests) the
+    buffers are staged through the host.  NCCL (one process per GPU) takes the device path."""
+    if send.is_cuda and dist.get_backend(group) == "gloo":
+        r = torch.empty(recv.shape, dtype=recv.dtype)
+        dist.all_gather_into_tensor(r, send.cpu(), group=group)
+        recv.copy_(r)
+    else:
+        dist.all_gather_into_tensor(recv, send, group=group)
+
+
 def build_chains(relations) -> List[List[int]]:
     """Group relation indices into chains (rel j follows rel i when first(j) == second(i)); order inside a chain and
     the order of chains follow the relation list."""
@@ -170,7 +181,7 @@ def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8,
         # ---- the one exchange of the path: all-gather of the scale vectors ------------------------------------------
         if world > 1:
             gathered = torch.empty(world * n_rel * slot, dtype=torch.float32, device=sess.device)
-            dist.all_gather_into_tensor(gathered, S_all.reshape(-1).contiguous(), group=group)
+            _all_gather_flat(gathered, S_all.reshape(-1).contiguous(), group)
             gathered = gathered.view(world, n_rel, slot)
             rel_owner = [0] * n_rel
             for c, ch in enumerate(chains):
@@ -268,7 +279,7 @@ def sharded_bias_correction(graph, bottoms, targ_type, bits_weight=8, bn_type=to
                 if it["next_bn_b_off"] >= 0:
                     send[k, 1, :it["rows"]] = sess.view(it["next_bn_b_off"], it["rows"])
             recv = torch.empty(world * cap * 2 * slot, dtype=torch.float32, device=sess.device)
-            dist.all_gather_into_tensor(recv, send.reshape(-1), group=group)
+            _all_gather_flat(recv, send.reshape(-1), group)
             recv = recv.view(world, cap, 2, slot)
             for r in range(world):
                 if r == rank:

@@ -46,12 +46,34 @@ def main():
         if type(ma) in targ:
             a, b = ma.weight.detach().double(), mb.weight.detach().double()
             worst = max(worst, float((a - b).abs().max() / a.abs().max().clamp_min(1e-30)))
-    flag = torch.tensor([1.0 if (s_equal or mode != "exact") and worst <= 1e-5 else 0.0], device="cuda")
+    # bias correction: single process on the single-GPU result vs sharded_bias_correction on the sharded result (both models are
+    # equal at this point up to the replay tolerance above; the correction itself must agree to 1e-5)
+    ga2, ba2, _ = workload.build_graph(topo, seed=0)
+    LT.merge_batchnorm(None, ga2, ba2, targ)
+    ra2 = create_relation(ga2, ba2, targ)
+    dfq.cross_layer_equalization(ga2, ra2, targ)
+    gb2, bb2, _ = workload.build_graph(topo, seed=0)
+    LT.merge_batchnorm(None, gb2, bb2, targ)
+    rb2 = create_relation(gb2, bb2, targ)
+    dfq.cross_layer_equalization(gb2, rb2, targ)               # identical starting points for the correction
+    dfq.bias_correction(ga2, ba2, targ)
+    binfo = ddist.sharded_bias_correction(gb2, bb2, targ, replicate_below=1 << 18)
+    worst_b = 0.0
+    for (ka, ma), (kb, mb) in zip(ga2.items(), gb2.items()):
+        if type(ma) in targ and ma.bias is not None:
+            a, b = ma.bias.detach().double(), mb.bias.detach().double()
+            worst_b = max(worst_b, float((a - b).abs().max() / a.abs().max().clamp_min(1e-30)))
+        if hasattr(ma, "fake_bias") and not isinstance(ma, str):
+            a, b = ma.fake_bias.double(), mb.fake_bias.double()
+            worst_b = max(worst_b, float((a - b).abs().max() / a.abs().max().clamp_min(1e-30)))
+    flag = torch.tensor([1.0 if (s_equal or mode != "exact") and worst <= 1e-5 and worst_b <= 1e-5 else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         owners = np.bincount(np.asarray(info["owner"]), minlength=world).tolist()
-        print("dist_check %s mode=%s world=%d: chains per rank %s, sweeps %s, S bit-identical %s, worst weight normwise %.3g -> %s"
-              % (name, mode, world, owners, info["sweeps"], s_equal, worst, "OK" if flag.item() == 1.0 else "MISMATCH"))
+        print("dist_check %s mode=%s world=%d: chains per rank %s, sweeps %s, S bit-identical %s, worst weight normwise %.3g; "
+              "bias correction: %d levels (%d sharded), worst bias/fake_bias normwise %.3g -> %s"
+              % (name, mode, world, owners, info["sweeps"], s_equal, worst, binfo["levels"], binfo["sharded_levels"], worst_b,
+                 "OK" if flag.item() == 1.0 else "MISMATCH"))
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
