@@ -33,9 +33,8 @@
 
 namespace dfq {
 
-// 7 consumer warps + the producer = 8 warps = two per SM sub-partition: k_bc_stream's register-resident path needs 224
-// registers per thread, and a sub-partition's 16 K registers hold exactly two such warps (a ninth warp does not fit).
-// Measured on the stack (bias_correct ms at 4096 pairs, shared-memory path): 4 consumers 4.88, 5: 4.89, 6: 4.31-4.54, 7: 4.15, 8: 4.76.
+// 7 consumer warps + the producer = 8 warps = two per SM sub-partition; 11 - 7 = 4 stages loading while all consumers compute.
+// Measured on the stack (bias_correct ms at 4096 pairs): 4 consumers 4.88, 5: 4.89, 6: 4.31-4.54, 7: 4.15, 8: 4.76.
 #ifndef DFQ_BC_CONSUMERS
 #define DFQ_BC_CONSUMERS 7
 #endif

@@ -521,6 +521,9 @@ struct PassIter {
   TileCursor cur;
   int q_live;   // last task whose group was checked and found still iterating (one uncached read per layer, not per tile)
   int g_seen, g_done;   // ... and per run of layers of the same group, not per layer
+  // shape of the layer in hand, fetched once per layer: fill() runs in the single producer lane for EVERY tile, and a 64-byte
+  // descriptor load from global memory there (~0.4 us of L2 latency) was what k_cle_stack waited for (round 2)
+  int f_q; int f_li, f_rows, f_row_len; long long f_w_off;
   __device__ __forceinline__ void settle() {
     while (cur.valid()) {
       if (cur.t >= q_hi) {
@@ -537,7 +540,7 @@ struct PassIter {
     }
   }
   __device__ __forceinline__ void start(const long long* p, const int* sl, const DfqLayer* L_, const GroupState* G_, int qb, int qe) {
-    ptr = p; step_layers = sl; L = L_; G = G_; q_end = qe; q_live = -1; g_seen = -1; g_done = 0;
+    ptr = p; step_layers = sl; L = L_; G = G_; q_end = qe; q_live = -1; g_seen = -1; g_done = 0; f_q = -1;
     cur.init(p[qb], p[qe]);
     q = cur.valid() ? find_task(p, qb, qe, cur.t) : qb;
     q_lo = p[q]; q_hi = (q < qe) ? p[q + 1] : p[q];
@@ -545,16 +548,19 @@ struct PassIter {
   }
   __device__ __forceinline__ bool valid() const { return cur.valid(); }
   __device__ __forceinline__ void next() { cur.next(); settle(); }
-  __device__ __forceinline__ void fill(TileDesc& d, float* arena) const {
-    const int li = step_layers[q];
-    const DfqLayer l = L[li];
-    const int row_len = l.cols * l.kk;
+  __device__ __forceinline__ void fill(TileDesc& d, float* arena) {
+    if (q != f_q) {
+      f_q = q; f_li = step_layers[q];
+      const DfqLayer l = L[f_li];
+      f_rows = l.rows; f_row_len = l.cols * l.kk; f_w_off = l.w_off;
+    }
+    const int li = f_li, row_len = f_row_len;
     const int rpt = pipe_rows_per_tile(row_len);
     d.task = li;
     d.row0 = (int)(cur.t - q_lo) * rpt;
-    d.nrows = min(rpt, l.rows - d.row0);
+    d.nrows = min(rpt, f_rows - d.row0);
     d.floats = d.nrows * row_len;
-    d.gptr = arena + l.w_off + (size_t)d.row0 * row_len;
+    d.gptr = arena + f_w_off + (size_t)d.row0 * row_len;
     if (row_len > kStageFloats) d.kind = TK_DIRECT;
     else d.kind = (((((uintptr_t)d.gptr) & 15) == 0) && ((d.floats & 3) == 0)) ? TK_BULK : TK_PLAIN;
   }
@@ -1066,11 +1072,12 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
           const int row_len = c.row_len, n4 = row_len >> 2;
           const uint32_t sbase = smem_u32(ring.stage(s));
           const double inv_n = c.inv_n;
-          if (c.has_out) {
+          RowIn mine; mine.cmn = mine.cmx = 0.f; mine.u = 1.f; mine.s_given = 1.f;
+          float ks = 1.f, kinv = 1.f;
+          const bool has_out = c.has_out != 0;
+          if (has_out) {
             // ---- first layer of a chain: per-row range -> s -> rescale (dfq.py:48-73) --------------------------------
-            RowIn mine; mine.cmn = mine.cmx = 0.f; mine.u = 1.f; mine.s_given = 1.f;
             if (lane < d.nrows) mine = fetch_row_in(c, P, d.row0 + lane, false);     // this lane's row: column extrema of the pair
-            float ks = 1.f, kinv = 1.f;
             for (int r = 0; r < d.nrows; ++r) {
               const uint32_t a0 = sbase + (uint32_t)r * (uint32_t)row_len * 4u;
               float mn = DFQ_INF, mx = -DFQ_INF;
@@ -1098,7 +1105,6 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
               }
               dacc += (double)dsum * inv_n;
             }
-            if (lane < d.nrows) publish_row(c, P, d.row0 + lane, ks, kinv, mine.cmn, mine.cmx);
           } else {
             // ---- second layer: columns scaled by 1/s of the relation (dfq.py:73) ------------------------------------
             for (int r = 0; r < d.nrows; ++r) {
@@ -1136,6 +1142,9 @@ k_cle_stack(float* arena, const DfqLayer* __restrict__ L, int nL, const DfqRelat
             bulk_wait_read<0>();
             mbar_arrive(ring.empty + s);
           }
+          // per-channel bookkeeping of dfq.py:62-70 (S, 1/s, bias, BN vectors, derived column extrema), lane r for row r - after
+          // the stage is on its way back: a dozen dependent global accesses that the ring does not have to wait for
+          if (has_out && lane < d.nrows) publish_row(c, P, d.row0 + lane, ks, kinv, mine.cmn, mine.cmx);
         }
         flush_metric();
         if (lane == 0) { bulk_wait_all(); fence_proxy_async_all(); }

@@ -521,7 +521,7 @@ __device__ __forceinline__ void bc_feed(BcRing& ring, unsigned long long& n, con
   for (int i = 0; i < kBcConsumers; ++i) bc_produce(ring, n++, d);
 }
 
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(kBcThreads, 1)
 k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __restrict__ B, int nB,
             const DfqExpectTerm* __restrict__ T, const int* __restrict__ level_ptr, int n_levels, int num_bits,
             const long long* __restrict__ row_ptr, const long long* __restrict__ mm_ptr) {
@@ -634,44 +634,10 @@ k_bc_stream(float* arena, const DfqLayer* __restrict__ L, const DfqBcLayer* __re
           if (b.next_bn_b_off >= 0) old_next = __ldcg(arena + b.next_bn_b_off + d.row0 + lane);
         }
         const uint32_t sbase = smem_u32(ring.stage(s));
-        // ---- register-resident fast path: a [512,3,3] row (the synthetic stack / ResNet's widest layers) ------------------
-        // The warp copies its row into registers (144 per lane) and hands the stage back BEFORE it computes: a stage is
-        // then occupied for the copy only, and (almost) all of the ring is loading - round 2's profile of the previous
-        // version showed half of the warp samples waiting for data with 8 of 11 stages held by computing warps.
-        if (mode == 0 && excached && d.kind == TK_BULK && d.nrows == 1 && l.kk == 9 && l.cols == 512) {
-          const int g = d.row0 / so;
-          if (g != cur_group) {
-            cur_group = g;
-            const float* ex = arena + b.expect_off + (size_t)g * l.cols;
-            __syncwarp();
-            for (int j = lane; j < l.cols; j += 32) exs[j] = __ldcg(ex + j);
-            __syncwarp();
-          }
-          float w[16][9];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const uint32_t a = sbase + (uint32_t)(lane + 32 * c) * 36u;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) w[c][k] = lds_f32(a + 4u * k);
-          }
-          bc_give_back(ring, s, lane);                     // the row is in registers: the stage can be refilled now
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float E = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) E = __fadd_rn(E, bc_qerr_own_range(w[c][k], f));
-            acc = __fma_rn((double)E, (double)exs[lane + 32 * c], acc);
-          }
-          acc = warp_sum(acc);
-          if (lane == 0) {
-            const float dl0 = (float)acc;
-            __stcg(arena + b.delta_off + d.row0, dl0);
-            __stcg(arena + l.bias_off + d.row0, __fadd_rn(old_bias, (b.flags & 2) ? dl0 : -dl0));                 // dfq.py:292 / :164
-            if (b.next_bn_b_off >= 0) __stcg(arena + b.next_bn_b_off + d.row0, __fadd_rn(old_next, -dl0));      // dfq.py:204-206,293
-          }
-          continue;
-        }
+        // (Tried: copying a [512,3,3] row to registers - 144 per lane, 224 registers per thread - and handing the stage back
+        // BEFORE the arithmetic, so that the whole ring is loading.  The straight-line code that needs (16 columns x 9 taps
+        // fully unrolled, ~1900 instructions, every warp at a different place in it) misses the instruction cache like the very
+        // first version of this kernel did: 1.31 ms instead of 1.14 ms at 1024 pairs.  The rolled shared-memory loop stays.)
         for (int r = 0; r < d.nrows; ++r) {
           const int g = (d.row0 + r) / so;
           const float* ex = arena + b.expect_off + (size_t)g * l.cols;

@@ -184,8 +184,12 @@ struct MatIter {
   int q, q_end;
   TileCursor cur;
   Geo geo;
+  // geometry of task `gq`, fetched once per task: geo() chases two dependent global loads (task -> layer -> shape), and the
+  // single producer lane of a streaming kernel would otherwise pay that latency (~0.6 us) for EVERY tile it issues
+  int gq;
+  float* g_base; int g_rows, g_row_len;
   __device__ __forceinline__ void start(const long long* p, int q_begin, int q_end_, Geo g) {
-    ptr = p; q_end = q_end_; geo = g;
+    ptr = p; q_end = q_end_; geo = g; gq = -1; g_base = nullptr; g_rows = g_row_len = 0;
     cur.init(p[q_begin], p[q_end_]);
     q = cur.valid() ? find_task(p, q_begin, q_end_, cur.t) : q_begin;
   }
@@ -194,9 +198,9 @@ struct MatIter {
     cur.next();
     while (q + 1 < q_end && ptr[q + 1] <= cur.t) ++q;
   }
-  __device__ __forceinline__ void fill(TileDesc& d) const {
-    float* base; int rows, row_len;
-    geo(q, base, rows, row_len);
+  __device__ __forceinline__ void fill(TileDesc& d) {
+    if (q != gq) { geo(q, g_base, g_rows, g_row_len); gq = q; }
+    float* base = g_base; const int rows = g_rows, row_len = g_row_len;
     const int rpt = pipe_rows_per_tile(row_len);
     d.task = q;
     d.row0 = (int)(cur.t - ptr[q]) * rpt;
