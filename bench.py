@@ -91,11 +91,12 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": reasons}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_cle_engine from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full_1024layers.md: 19.375 GB read + 19.434 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The kernel's traffic is linear
-# in the number of pairs (every block is identical), so the figure is scaled to the benched size; None for other sweep counts.
-NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.809e9
-NCU_TRAFFIC_SOURCE = "ncu --set full capture at 1024 pairs (profiles/r1_ncu_full_1024layers.md), scaled linearly to the benched pairs"
+# dram__bytes_read.sum + dram__bytes_write.sum of the equalization kernel (k_cle_stack) from the committed `ncu --set full`
+# capture (profiles/r2_cle_stack_v1.md: 19.350 GB read + 19.300 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The
+# kernel's traffic is linear in the number of pairs (every block is identical), so the figure is scaled to the benched size;
+# None for other sweep counts.  (k_cle_engine, round 1: 38.809 GB, profiles/r1_ncu_full_1024layers.md.)
+NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.650e9
+NCU_TRAFFIC_SOURCE = "ncu --set full capture of k_cle_stack at 1024 pairs (profiles/r2_cle_stack_v1.md), scaled linearly to the benched pairs"
 
 
 def ncu_traffic(layers, sweeps):
@@ -463,7 +464,7 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     cle_bytes = 8.0 * N_PER_LAYER * layers * res.n_sweeps          # 8 B per weight per sweep
     achieved = cle_bytes / (ms_cle * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_cle_engine", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_cle_stack (equalization of the two-layer chains; k_cle_engine when DFQ_CLE_STACK=0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(layers, res.n_sweeps), "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_launch": cle_bytes, "ms_per_launch": ms_cle,
                 "whole_step": {"algorithmic_bytes": (26.0 + (12.0 if args.quantize else 0)) * N_PER_LAYER * layers,

@@ -98,7 +98,7 @@ struct BcRing {
     empty = (uint64_t*)(p + 8 * kBcStages);
     desc = (TileDesc*)(p + 16 * kBcStages + 16);
     if (threadIdx.x == 0) {
-      for (int i = 0; i < kBcStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+      for (int i = 0; i < kBcStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); desc[i].seq = -1; }
       mbar_fence_init();
     }
     __syncthreads();
@@ -116,6 +116,7 @@ __device__ __forceinline__ void bc_produce(BcRing& ring, unsigned long long n, c
   const int s = (int)(n % kBcStages);
   if (n >= kBcStages) mbar_wait(ring.empty + s, (uint32_t)(((n / kBcStages) - 1) & 1));
   ring.desc[s] = d;
+  ring.desc[s].seq = (int)n;            // before the arrive below: visible to whoever sees the phase complete
   if (d.kind == TK_BULK) {
     mbar_arrive_expect_tx(ring.full + s, (uint32_t)d.floats * 4u);
     bulk_g2s(ring.stage(s), d.gptr, (uint32_t)d.floats * 4u, ring.full + s);
@@ -125,9 +126,21 @@ __device__ __forceinline__ void bc_produce(BcRing& ring, unsigned long long n, c
 }
 
 // Consumer side: wait for item n; returns its stage.
+//
+// A parity wait alone is NOT enough here.  `mbarrier.try_wait.parity p` answers "has the phase with parity p completed?" by
+// comparing p with the barrier's current phase parity - which is only meaningful when the waiter is at most one phase away.
+// Consumers of this ring own different stages in turn (the stage count is not a multiple of the consumer count), so the warp
+// that is about to wait for use u of stage s may get there while use u-1 of that stage - another warp's item, issued 11 items
+// earlier - is still LOADING: the barrier is then in phase u-1, its parity differs from u's, and try_wait returns "done" at
+// once.  The warp would process the previous tile's stage a second time and arrive on `empty` a second time (round 2: "Warp
+// Illegal Instruction" at the producer's next arrive, hangs, on stacks of 16-96 blocks whose loads start cold; steady-state
+// runs of 1000+ blocks never hit it).  The producer therefore stamps every item with its sequence number before it arrives,
+// and the consumer first waits (polling shared memory) until the stage holds ITS item, then for the barrier.
 __device__ __forceinline__ int bc_take(BcRing& ring, unsigned long long n) {
   const int s = (int)(n % kBcStages);
-  mbar_wait(ring.full + s, (uint32_t)((n / kBcStages) & 1));
+  const volatile int* seq = &ring.desc[s].seq;
+  while (*seq != (int)n) __nanosleep(32);     // the producer has put MY item into the stage: use u-1 is over, the barrier is in phase u
+  mbar_wait(ring.full + s, (uint32_t)((n / kBcStages) & 1));      // ... and its bytes have landed
   return s;
 }
 __device__ __forceinline__ void bc_give_back(BcRing& ring, int s, int lane) {

@@ -511,7 +511,10 @@ static_assert(kPipeMaxRows <= 32, "a consumer warp retires one row per lane");
 __device__ __forceinline__ void bc_feed(BcRing& ring, unsigned long long& n, const long long* ptr, int q_begin, int q_end,
                                         const BcGeo& geo) {
   TileDesc d;
-  MatIter<BcGeo> it;
+#ifndef DFQ_BC_FEED_CACHE
+#define DFQ_BC_FEED_CACHE 1
+#endif
+  MatIter<BcGeo, DFQ_BC_FEED_CACHE != 0> it;
   it.start(ptr, q_begin, q_end, geo);
   while (it.valid()) { it.fill(d); bc_produce(ring, n++, d); it.next(); }
   d.gptr = nullptr; d.task = -1; d.row0 = d.nrows = d.floats = 0;

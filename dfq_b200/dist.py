@@ -94,9 +94,16 @@ def _replay_exit_rule(diffs: Sequence[float], converge_thres: float, converge_co
 
 
 def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8, 1e8), converge_thres=2e-7,
-                                     converge_count=20, signed=False, eps=0, mode="per_chain", group=None, max_record=64):
+                                     converge_count=20, signed=False, eps=0, mode="per_chain", group=None, max_record=64,
+                                     replicas="replay"):
     """cross_layer_equalization (dfq.py:78-117) with the chains sharded over the ranks of `group`.
     Every rank must call it with the same graph/relations; every rank's model ends up fully equalized.
+    replicas="replay": only the scale vectors are exchanged and every rank replays the S of the chains it does not own
+                       (weights within ~3e-6 of the owner's; no weight crosses NVLink - the stack-sized workloads);
+    replicas="exact":  the all-gathered buffer ALSO carries the equalized weights / biases / BN vectors of every rank's chains
+                       (a real model: a few tens of MB), so every rank ends with bit-identical parameters - what the steps
+                       downstream of the equalization need when they are ill-conditioned in the last bit of the weights
+                       (bias correction) and every rank must reach the same model.
     Returns dict(owner=[rank per chain], sweeps=..., chains=...)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -189,11 +196,41 @@ def sharded_cross_layer_equalization(graph, relations, targ_type, s_range=(1e-8,
                     rel_owner[i] = owner[c]
             S_all = torch.stack([gathered[rel_owner[i], i] for i in range(n_rel)])
             others = [i for i in range(n_rel) if rel_owner[i] != rank]
-            if others:
-                rplan = sess.plan_cle([table[i] for i in others])
-                for i, off in zip(others, rplan["s_offs"]):
-                    sess.view(off, chan[i]).copy_(S_all[i, :chan[i]])
-                sess.run_cle_plan(rplan, s_range, signed=signed, eps=eps, apply_only=True)
+            if replicas == "exact":
+                # every tensor a chain's equalization writes: weights and biases of its layers, fake_weight / fake_bias of its BNs
+                def chain_views(c):
+                    seen, out = set(), []
+                    for i in chains[c]:
+                        l1, l2, obw, obb = table[i]
+                        for li in (l1, l2):
+                            if li not in seen:
+                                seen.add(li)
+                                l = sess.layer(li)
+                                out.append((l["w_off"], l["rows"] * l["cols"] * l["kk"])); out.append((l["bias_off"], l["rows"]))
+                        out.append((obw, chan[i])); out.append((obb, chan[i]))
+                    return out
+                per_rank = [[v for c in range(len(chains)) if owner[c] == r for v in chain_views(c)] for r in range(world)]
+                cap = max(sum(n for _, n in vs) for vs in per_rank)
+                send = torch.zeros(cap, dtype=torch.float32, device=sess.device)
+                o = 0
+                for off, n in per_rank[rank]:
+                    send[o:o + n].copy_(sess.view(off, n)); o += n
+                recv = torch.empty(world * cap, dtype=torch.float32, device=sess.device)
+                _all_gather_flat(recv, send, group)
+                for r in range(world):
+                    if r == rank:
+                        continue
+                    o = r * cap
+                    for off, n in per_rank[r]:
+                        sess.view(off, n).copy_(recv[o:o + n]); o += n
+            elif replicas == "replay":
+                if others:
+                    rplan = sess.plan_cle([table[i] for i in others])
+                    for i, off in zip(others, rplan["s_offs"]):
+                        sess.view(off, chan[i]).copy_(S_all[i, :chan[i]])
+                    sess.run_cle_plan(rplan, s_range, signed=signed, eps=eps, apply_only=True)
+            else:
+                raise ValueError(replicas)
         sess.download()
         for i, rr in enumerate(relations):
             S = S_all[i, :chan[i]].clone()

@@ -2,9 +2,11 @@
 
 Four worker processes share cuda:0 (gloo for the rendezvous and the collectives - NCCL refuses several ranks on one device;
 the collectives' payloads are staged through the host in that case, dfq_b200/dist.py::_all_gather_flat), every rank runs the
-REAL kernels on its shard: chain-sharded equalization in `exact` mode + the single all-gather of the scale vectors + replay,
-then sharded bias correction.  Every rank must end with the model a single process computes on the same GPU: S bit for bit,
-weights within 1e-5 (replicas replay the accumulated scale in one multiplication), biases / fake_bias within 1e-5.
+REAL kernels on its shard: chain-sharded equalization in `exact` mode + ONE all-gather (scale vectors and, replicas="exact",
+the owners' equalized tensors), then sharded bias correction.  Every rank must end with the model a single process computes
+on the same GPU: S, weights bit for bit, biases / fake_bias within 1e-5.  (With replicas="replay" the weights of non-owned
+chains are within ~3e-6 and - bias correction being ill-conditioned in the last bit of the weights, DESIGN.md section 4 - the
+biases only within 5e-2: the second test.)
 The NCCL flavour of the same check (one process per GPU) is tools/dist_check.py, profiles/r2_dist_check.txt."""
 import os
 import sys
@@ -24,7 +26,7 @@ def _nw(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
-def _calibrate(sharded, name="deeplab"):
+def _calibrate(sharded, name="deeplab", replicas="exact"):
     import torch.nn as nn
     from dfq_b200 import dfq, workload, dist as ddist
     from dfq_b200.utils import layer_transform as LT
@@ -36,7 +38,7 @@ def _calibrate(sharded, name="deeplab"):
     rels = create_relation(graph, bottoms, targ)
     info = {}
     if sharded:
-        info = ddist.sharded_cross_layer_equalization(graph, rels, targ, mode="exact")
+        info = ddist.sharded_cross_layer_equalization(graph, rels, targ, mode="exact", replicas=replicas)
         info["bc"] = ddist.sharded_bias_correction(graph, bottoms, targ, replicate_below=1 << 18)
     else:
         dfq.cross_layer_equalization(graph, rels, targ)
@@ -55,13 +57,13 @@ def _calibrate(sharded, name="deeplab"):
     return out, info
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, replicas):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     torch.cuda.set_device(0)
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
-        out, info = _calibrate(True)
+        out, info = _calibrate(True, replicas=replicas)
         out["owner"] = np.array(info["owner"])
         out["bc_sharded_levels"] = np.array(info["bc"]["sharded_levels"])
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **out)
@@ -70,11 +72,12 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(900)
-def test_deeplab_sharded_over_four_ranks_equals_one_process(tmp_path):
+@pytest.mark.parametrize("replicas", ["exact", "replay"])
+def test_deeplab_sharded_over_four_ranks_equals_one_process(replicas, tmp_path):
     world = 4
     single, _ = _calibrate(False)
-    port = 29500 + (os.getpid() % 2000) + 61
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + (61 if replicas == "exact" else 67)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), replicas), nprocs=world, join=True)
     worst_w = worst_b = 0.0
     for r in range(world):
         d = np.load(tmp_path / ("rank%d.npz" % r))
@@ -87,5 +90,9 @@ def test_deeplab_sharded_over_four_ranks_equals_one_process(tmp_path):
                 worst_w = max(worst_w, _nw(d[k], v))
             elif k[0] in "bf":
                 worst_b = max(worst_b, _nw(d[k], v))
-    print("DeepLab, 4 ranks: S bit-identical on every rank, worst weight %.3g, worst bias/fake_bias %.3g (normwise)" % (worst_w, worst_b))
-    assert worst_w <= 1e-5 and worst_b <= 1e-5, (worst_w, worst_b)
+    print("DeepLab, 4 ranks, replicas=%s: S bit-identical on every rank, worst weight %.3g, worst bias/fake_bias %.3g (normwise)"
+          % (replicas, worst_w, worst_b))
+    if replicas == "exact":
+        assert worst_w == 0.0 and worst_b <= 1e-5, (worst_w, worst_b)
+    else:
+        assert worst_w <= 1e-5 and worst_b <= 5e-2, (worst_w, worst_b)

@@ -102,6 +102,9 @@ def test_pipeline_cuda_vs_reference_fixture(name, seed, signed):
         for j, i in enumerate(tl):
             w = real[tag]["w%d" % i]
             assert abs(np.abs(w).max() - gold[tag + "_w_absmax"][j]) <= 1e-5 * gold[tag + "_w_absmax"][j]
+            # ... and the fp64 sum of the whole tensor (the fixtures hold max|w|, the sum and a sha256 per tensor, not the
+            # tensors): 1e-5 of sum|w|, i.e. a systematic error of 1e-5 in any row or column would show
+            assert abs(w.astype(np.float64).sum() - gold[tag + "_w_sum"][j]) <= 1e-5 * np.abs(w).astype(np.float64).sum(), (tag, j)
             if "%s_bias_%d" % (tag, i) in gold.files:
                 assert _nw(real[tag]["b%d" % i], gold["%s_bias_%d" % (tag, i)]) < 1e-5
         for k in real[tag]:
