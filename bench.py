@@ -425,7 +425,20 @@ def run_b200(args, rank, world, local_rank):
                   "bias_max_normwise_error": max(c["bias_normwise"] for c in checks),
                   "sweeps_equal_oracle": all(c["sweeps"] == int(res.group_sweeps[b]) for c, b in zip(checks, sorted({0, n_blocks - 1}))),
                   "oracle": "oracle/stack_check.py on the pristine bits of the timed stack, after the last timed step"}
-        parity["ok"] = bool(parity["weights_bit_exact"] and parity["bias_max_normwise_error"] < 1e-5 and parity["sweeps_equal_oracle"])
+        # ... and a size-independent property over EVERY block of the stack (torch reductions on the device): after the
+        # equalization the range of row c of the first conv equals the range of input column c of the second conv
+        # (s = sqrt(r2/r1) makes both sqrt(r1*r2), dfq.py:58), and nothing is non-finite
+        w = after[:2 * n_blocks * N_PER_LAYER].view(n_blocks, 2, C, C, K * K)
+        dev_max = 0.0
+        for lo in range(0, n_blocks, 256):
+            a, b2 = w[lo:lo + 256, 0], w[lo:lo + 256, 1]
+            r1 = a.amax(dim=(2, 3)) - a.amin(dim=(2, 3))
+            r2 = b2.amax(dim=(1, 3)) - b2.amin(dim=(1, 3))
+            dev_max = max(dev_max, float(((r1 - r2).abs() / r1).max()))
+        parity["all_blocks_range_mismatch"] = dev_max
+        parity["all_finite"] = bool(torch.isfinite(after).all())
+        parity["ok"] = bool(parity["weights_bit_exact"] and parity["bias_max_normwise_error"] < 1e-5 and parity["sweeps_equal_oracle"]
+                            and dev_max < 1e-5 and parity["all_finite"])
 
     t = torch.tensor([sum(sum(r) for r in timers) / len(timers),
                       sum(r[1] for r in timers) / len(timers)], dtype=torch.float64, device=dev)

@@ -145,10 +145,11 @@ class GraphCalibration:
         with torch.no_grad():
             sess.download()          # weights, biases, fake_weight / fake_bias and the scale vectors: one D2H copy
             eps = _identity_bn_eps()
-            for key, v in self._bn.items():
-                if v.get("folded"):
-                    bn = self.graph[key]
-                    bn.weight.fill_(1); bn.running_var.fill_(1); bn.bias.fill_(0); bn.running_mean.fill_(0)
+            folded = [self.graph[key] for key, v in self._bn.items() if v.get("folded")]
+            if folded:      # identity BN (layer_transform.py:268-272): four batched fills instead of four per layer
+                torch._foreach_fill_([bn.weight.detach() for bn in folded] + [bn.running_var for bn in folded], 1.0)
+                torch._foreach_fill_([bn.bias.detach() for bn in folded] + [bn.running_mean for bn in folded], 0.0)
+                for bn in folded:
                     bn.eps = eps
             if self._cle_plan is not None and self.last_cle is not None:
                 for rr, s in zip(self.relations, self._S_host):

@@ -325,6 +325,30 @@ def test_stack_kernel_equals_engine_on_other_block_shapes(channels, k, monkeypat
     assert torch.equal(outs[0][1], outs[1][1]), "S differs"
 
 
+@pytest.mark.parametrize("n_blocks", [16, 40])
+def test_mid_size_stacks_run_the_streaming_kernels_and_match_the_oracle(n_blocks):
+    """Regression for the ring's phase hazard (bc_stream.cuh::bc_take): stacks of 16-96 blocks - large enough for the streaming
+    kernels (k_cle_stack, k_bc_stream are chosen by the library, nothing is forced), small enough that every load starts cold -
+    crashed with 'Warp Illegal Instruction' or hung before consumers waited for their item's sequence stamp.  Three full steps
+    each, first and last block against the oracle."""
+    from dfq_b200.engine import Session
+    from dfq_b200.workload import DeviceStack
+    from oracle import stack_check
+    sess = Session()
+    st = DeviceStack(sess, n_blocks, 512, 3, seed=1000 + n_blocks)
+    st.generate()
+    pristine = st.state().clone()
+    for _ in range(3):
+        st.state().copy_(pristine)
+        res = st.run()
+        torch.cuda.synchronize()
+    assert res.converged and set(int(x) for x in res.group_sweeps) == {2}
+    after = st.state()
+    for b in (0, n_blocks - 1):
+        r = stack_check.compare_block(st.block_arrays(pristine, b), st.block_arrays(after, b))
+        assert r["weights_bit_exact"] and r["vectors_bit_exact"] and r["bias_normwise"] < 1e-5 and r["sweeps"] == 2, (b, r)
+
+
 def _config5_blocks():
     """The headline workload shape itself (BASELINE configs[4]): Conv[512,512,3,3]+BN+ReLU -> Conv[512,512,3,3]+BN blocks
     through the fused step bench.py times (fold with column scan -> equalization -> correction with range hints) vs the
