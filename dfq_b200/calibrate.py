@@ -147,8 +147,9 @@ class GraphCalibration:
             eps = _identity_bn_eps()
             folded = [self.graph[key] for key, v in self._bn.items() if v.get("folded")]
             if folded:      # identity BN (layer_transform.py:268-272): four batched fills instead of four per layer
-                torch._foreach_fill_([bn.weight.detach() for bn in folded] + [bn.running_var for bn in folded], 1.0)
-                torch._foreach_fill_([bn.bias.detach() for bn in folded] + [bn.running_mean for bn in folded], 0.0)
+                ones = [bn.weight.detach() for bn in folded] + [bn.running_var for bn in folded]
+                torch._foreach_zero_(ones + [bn.bias.detach() for bn in folded] + [bn.running_mean for bn in folded])
+                torch._foreach_add_(ones, 1.0)
                 for bn in folded:
                     bn.eps = eps
             if self._cle_plan is not None and self.last_cle is not None:
