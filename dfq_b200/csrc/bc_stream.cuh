@@ -135,12 +135,18 @@ __device__ __forceinline__ void bc_produce(BcRing& ring, unsigned long long n, c
 // once.  The warp would process the previous tile's stage a second time and arrive on `empty` a second time (round 2: "Warp
 // Illegal Instruction" at the producer's next arrive, hangs, on stacks of 16-96 blocks whose loads start cold; steady-state
 // runs of 1000+ blocks never hit it).  The producer therefore stamps every item with its sequence number before it arrives,
-// and the consumer first waits (polling shared memory) until the stage holds ITS item, then for the barrier.
+// and the consumer re-checks the stamp after every wait (and waits once more after it matched: the stamp is written before
+// the producer's arrive, so by then the barrier is in the right phase).
 __device__ __forceinline__ int bc_take(BcRing& ring, unsigned long long n) {
   const int s = (int)(n % kBcStages);
   const volatile int* seq = &ring.desc[s].seq;
-  while (*seq != (int)n) __nanosleep(32);     // the producer has put MY item into the stage: use u-1 is over, the barrier is in phase u
-  mbar_wait(ring.full + s, (uint32_t)((n / kBcStages) & 1));      // ... and its bytes have landed
+  const uint32_t parity = (uint32_t)((n / kBcStages) & 1);
+  for (;;) {                                   // common case: one hardware wait, one shared-memory compare
+    mbar_wait(ring.full + s, parity);
+    if (*seq == (int)n) break;                 // the stage holds MY item
+    __nanosleep(64);                           // spurious "done": the barrier was still one phase behind
+  }
+  mbar_wait(ring.full + s, parity);            // stamp seen => the barrier is in (or past) my phase: returns when the bytes have landed
   return s;
 }
 __device__ __forceinline__ void bc_give_back(BcRing& ring, int s, int lane) {
