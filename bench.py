@@ -490,14 +490,29 @@ def run_b200(args, rank, world, local_rank):
         chunk_blocks = max(1, args.e2e_chunk // 2)                # 32 layer pairs = 302 MB per chunk
         # 2 x 4.8 GB of page-locked memory per rank at 512 pairs, allocated on the rank's own NUMA node (bind_to_gpu_numa_node)
         e2e_pairs = args.e2e_layers
-        n_chunks = max(2, min(e2e_pairs, layers) // (2 * chunk_blocks))
-        e_layers = n_chunks * 2 * chunk_blocks
         del pristine
         torch.cuda.empty_cache()
         hc = HostStackCalibrator(dev, chunk_blocks, C, K, quantize=args.quantize, n_slots=args.e2e_slots)
-        n_state = hc.chunk_floats * n_chunks
-        host_in = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
-        host_out = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
+        # the box's page-locked budget is shared by all ranks: every rank tries the full sample and all ranks settle on the
+        # size the most constrained one got (halving on failure), so the ranks keep doing equal work
+        while True:
+            n_chunks = max(2, min(e2e_pairs, layers) // (2 * chunk_blocks))
+            n_state = hc.chunk_floats * n_chunks
+            try:
+                host_in = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
+                host_out = torch.empty(n_state, dtype=torch.float32, pin_memory=True)
+                ok = 1
+            except RuntimeError:
+                host_in = host_out = None
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1 or n_chunks <= 2:
+                break
+            host_in = host_out = None
+            e2e_pairs //= 2
+        e_layers = n_chunks * 2 * chunk_blocks
         for st_ in hc.slots:
             st_.generate()
         for i in range(n_chunks):                                 # synthetic host image (chunks repeat two seeds)
