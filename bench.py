@@ -179,7 +179,17 @@ def bind_to_gpu_numa_node(local_rank):
         if not cpus:
             return None
         os.sched_setaffinity(0, cpus)
-        return {"node": node, "cpus": len(cpus)}
+        policy = None
+        try:      # memory too: set_mempolicy(MPOL_PREFERRED, node) - page-locked allocations made by driver threads follow it
+            import ctypes
+            import platform
+            if platform.machine() == "x86_64" and node < 64:
+                mask = ctypes.c_ulong(1 << node)
+                if ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 65) == 0:
+                    policy = "preferred"
+        except Exception:
+            pass
+        return {"node": node, "cpus": len(cpus), "mempolicy": policy}
     except Exception:
         return None
 
@@ -531,12 +541,29 @@ def run_b200(args, rank, world, local_rank):
             e2e_step()
         e1.record()
         barrier()
-        tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        # the same chunks through the same streams WITHOUT the kernels: what the box's PCIe + host memory give this traffic
+        # pattern with all ranks copying at once (the ceiling of the e2e arm)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hc.run(host_in, host_out, copy_only=True)
+        barrier()
+        c0.record()
+        for _ in range(2):
+            hc.run(host_in, host_out, copy_only=True)
+        c1.record()
+        barrier()
+        mine = torch.tensor([e0.elapsed_time(e1) / args.steps, c0.elapsed_time(c1) / 2], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros_like(mine) for _ in range(world)] if world > 1 else [mine]
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_gather(per_rank, mine)
+        tt = torch.stack(per_rank).max(dim=0).values
         e2e = {"value": world * e_layers / (float(tt[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * n_state,
                "d2h_bytes_per_step": 4 * n_state, "layers_per_step": e_layers, "ms_per_step": float(tt[0]),
                "pcie_GBps_each_way": 4e-9 * n_state / (float(tt[0]) * 1e-3),
+               "pcie_GBps_each_way_per_rank": [round(4e-9 * n_state / (float(t[0]) * 1e-3), 2) for t in per_rank],
+               "copy_only": {"ms_per_step": float(tt[1]), "GBps_each_way": 4e-9 * n_state / (float(tt[1]) * 1e-3),
+                             "GBps_each_way_per_rank": [round(4e-9 * n_state / (float(t[1]) * 1e-3), 2) for t in per_rank],
+                             "what": "the same chunks through the same three streams with no kernel launched, all ranks "
+                                     "copying at once: the transfer ceiling of this box for the e2e arm"},
                "api": "dfq_b200.workload.HostStackCalibrator.run(pinned_in, pinned_out): %d-pair chunks, H2D / kernels / "
                       "D2H pipelined on three streams over %d arena slots" % (2 * chunk_blocks, args.e2e_slots)}
         del hc, host_in, host_out

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("DFQ_LIB_OUT") or os.path.join(HERE, "libdfq_sm100.so")
-SOURCES = ["tensor_ops.cu", "cle_engine.cu", "passes.cu", "distill.cu"]
+SOURCES = ["tensor_ops.cu", "cle_engine.cu", "passes.cu", "distill.cu", "host_copy.cu"]
 HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "rowpipe.cuh", "colscan.cuh", "bc_stream.cuh")] + \
     [os.path.join(HERE, "..", "include", "dfq_b200.h")]
 

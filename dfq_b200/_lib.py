@@ -111,6 +111,7 @@ SIGNATURES = {
     "dfq_quant_error": [_PF, _PF, _I64, _PF, C.c_int, C.c_int, _ST],
     "dfq_selftest_bc_arithmetic": [_PF, _PF, _PF, _I64, _PF, C.c_int, C.c_int, C.c_void_p, _ST],
     "dfq_clamp": [_PF, _I64, C.c_float, C.c_float, _ST],
+    "dfq_host_copy_segments": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int],
 }
 
 _lib = None

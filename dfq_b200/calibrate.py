@@ -143,7 +143,7 @@ class GraphCalibration:
     def download(self):
         sess = self.sess
         with torch.no_grad():
-            sess.download()          # weights, biases, fake_weight / fake_bias and the scale vectors: one D2H copy
+            sess.download_begin()    # weights, biases, fake_weight / fake_bias and the scale vectors: one D2H copy ...
             eps = _identity_bn_eps()
             folded = [self.graph[key] for key, v in self._bn.items() if v.get("folded")]
             if folded:      # identity BN (layer_transform.py:268-272): four batched fills instead of four per layer
@@ -152,6 +152,7 @@ class GraphCalibration:
                 torch._foreach_add_(ones, 1.0)
                 for bn in folded:
                     bn.eps = eps
+            sess.download_end()      # ... that crosses PCIe while the identity fills above run on the host
             if self._cle_plan is not None and self.last_cle is not None:
                 for rr, s in zip(self.relations, self._S_host):
                     rr.S = None

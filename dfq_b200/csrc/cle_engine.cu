@@ -697,6 +697,9 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
   __shared__ __align__(16) float s_inv_all[kTeams][kInvCache + 4];   // 1/s of the current layer's input columns
   struct RescanCtx { float *dmin, *dmax; int nch, go, gi; bool smem, own, single; };
   __shared__ RescanCtx rsx_all[kTeams];
+  __shared__ double s_rule_diff;          // single-group exit rule, replicated per CTA: `diff`, `count` of dfq.py:81-82
+  __shared__ int s_rule_count, s_rule_stop;
+  if (threadIdx.x == 0) { s_rule_diff = 10.0; s_rule_count = 0; s_rule_stop = 0; }
   const int tm = threadIdx.x < kTeams * kThreads ? team() : 0;
   RescanCtx& rsx = rsx_all[tm];
   float* red = red_all[tm];
@@ -933,8 +936,34 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
       grid.sync();
       mark();
     }
-    // ---- exit rule of dfq.py:105-115, one thread per group ------------------------------------------------
+    // ---- exit rule of dfq.py:105-115 -------------------------------------------------------------------------
     const int n = sweep + 1;
+    if (nG == 1) {
+      // ONE convergence group (a single model - the latency-bound case): every CTA evaluates the rule itself from the group's
+      // accumulator, complete since the last step's barrier - same inputs, same decision - instead of one thread deciding and
+      // a second grid barrier broadcasting it.  CTA 0 keeps the global record; the accumulator of sweep+2 is cleared here:
+      // its last readers (the rule of sweep-1) passed this sweep's barriers, its next writers wait behind the next ones.
+      if (threadIdx.x == 0) {
+        const double diff_tmp = *((volatile double*)&G[0].acc[slot]);
+        if (fabs(s_rule_diff - diff_tmp) > 1e-9) { s_rule_count = 0; s_rule_diff = diff_tmp; }
+        else s_rule_count++;
+        const bool cont = (s_rule_diff > P.converge_thres) && (s_rule_count < P.converge_count);
+        const int cap = P.max_sweeps > 0 ? P.max_sweeps : 4096;
+        const bool stop = !cont || n >= cap;
+        if (blockIdx.x == 0) {
+          GroupState& st = G[0];
+          st.acc[(slot + 2) % 3] = 0.0;
+          st.diff = s_rule_diff; st.count = s_rule_count;
+          if (sweep < 64) ctl->diffs[sweep] = diff_tmp;
+          if (stop) { st.n_sweeps = n; st.converged = !cont; st.done = 1; }
+        }
+        s_rule_stop = stop ? 1 : 0;
+      }
+      __syncthreads();
+      if (s_rule_stop) break;
+      __syncthreads();          // s_rule_stop is rewritten one sweep from now
+      continue;
+    }
     if (!producer) {
       for (int g = vblock() * kThreads + ctid(); g < nG; g += vgrid() * kThreads) {
         GroupState& st = G[g];

@@ -11,6 +11,7 @@ that already live on the GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -19,6 +20,13 @@ import torch
 
 from . import _lib
 from ._lib import DfqError
+
+# threads of the host gather/scatter (dfq_host_copy_segments); 0 = the library's default
+_HOST_COPY_THREADS = int(os.environ.get("DFQ_HOST_COPY_THREADS", "0"))
+# parts the upload of a model is cut into (gather of part i+1 overlaps the H2D copy of part i).  Measured on MobileNetV2
+# inside bench.py: 1 part 1.5 ms, 2 parts 1.4 ms, 4 parts 2.1 ms of upload() - the H2D copy (0.35 ms) is not worth hiding
+# behind extra library calls, so one part is the default.
+_UPLOAD_PARTS = int(os.environ.get("DFQ_UPLOAD_PARTS", "1"))
 
 
 _PIN = True       # page-locked staging buffers (tests that run the host logic without a GPU turn this off)
@@ -188,36 +196,86 @@ class Session:
         self._xfer = x
         return x
 
+    def _host_copy(self, x: dict, which: str, direction: int, i0: int = 0, i1: Optional[int] = None) -> bool:
+        """Gather (0) / scatter (1) between the bound host tensors [i0, i1) and the staging image with the library's
+        memcpy loop (dfq_host_copy_segments; ~0.6-1.4 ms for a MobileNetV2 instead of 1.6-2.0 ms of per-tensor copy
+        dispatch).  The addresses are read per call (a caller may have re-pointed a parameter's .data); returns False -
+        the caller then takes the tensor-library path - when a tensor is not a contiguous fp32 host tensor of the bound size."""
+        fn = getattr(self.lib, "dfq_host_copy_segments", None)
+        bounds = x[which + "_bounds"]
+        if fn is None or not bounds or self._staging is None:
+            return False
+        seg = x.get(which + "_seg")
+        if seg is None:
+            lo = x["lo"]
+            seg = x[which + "_seg"] = (np.array([4 * b.n for b in bounds], dtype=np.uint64),
+                                       np.array([4 * (b.off - lo) for b in bounds], dtype=np.uint64),
+                                       np.empty(len(bounds), dtype=np.uint64))
+        nbytes, offs, ptrs = seg
+        i1 = len(bounds) if i1 is None else i1
+        for i in range(i0, i1):
+            b = bounds[i]
+            t = b.tensor
+            if t.dtype != torch.float32 or t.numel() != b.n or not t.is_contiguous() or t.is_cuda:
+                return False
+            ptrs[i] = t.data_ptr()
+        _lib.check(fn(C.c_void_p(self._staging.data_ptr()), _lib.table_ptr(ptrs[i0:i1]), _lib.table_ptr(nbytes[i0:i1]),
+                      _lib.table_ptr(offs[i0:i1]), i1 - i0, direction, _HOST_COPY_THREADS), "dfq_host_copy_segments")
+        return True
+
+    def _upload_parts(self, x: dict):
+        """[(i0, i1, runs)]: the upload mirrors cut into a few parts of equal bytes - the H2D copy of one part crosses PCIe
+        while the host gathers the next one (a 14 MB model: 4 parts)."""
+        parts = x.get("h2d_parts")
+        if parts is None:
+            up = x["h2d_bounds"]
+            total = sum(b.n for b in up)
+            k = max(1, min(_UPLOAD_PARTS, (4 * total) >> 21))            # >= 2 MB per part
+            parts, i0, acc = [], 0, 0
+            for i, b in enumerate(up):
+                acc += b.n
+                if acc * k >= total * (len(parts) + 1) or i + 1 == len(up):
+                    parts.append((i0, i + 1, self._runs(up[i0:i + 1])))
+                    i0 = i + 1
+            x["h2d_parts"] = parts
+        return parts
+
     def upload(self):
         """Copy every bound tensor into the arena: host tensors through ONE pinned staging buffer and one H2D copy per
-        run of adjacent mirrors (a whole model: one), device tensors with device-to-device copies."""
+        run of adjacent mirrors, device tensors with device-to-device copies."""
         self._ensure_room()
         x = self._transfer_lists()
         with torch.no_grad():
             if x["h2d_bounds"]:
-                # (the sources are looked up per call: a caller may have re-pointed a parameter's .data since the last one)
-                torch._foreach_copy_(x["h2d_dst"], [b.tensor.detach().reshape(-1) for b in x["h2d_bounds"]])
                 lo, st = x["lo"], self._staging
-                for a, e in x["h2d_runs"]:
-                    self.arena[a:e].copy_(st[a - lo: e - lo], non_blocking=True)
-                    self.h2d_bytes += 4 * (e - a)
+                # (the sources are looked up per call: a caller may have re-pointed a parameter's .data since the last one)
+                for i0, i1, runs in self._upload_parts(x):
+                    if not self._host_copy(x, "h2d", 0, i0, i1):
+                        torch._foreach_copy_(x["h2d_dst"][i0:i1], [b.tensor.detach().reshape(-1) for b in x["h2d_bounds"][i0:i1]])
+                    for a, e in runs:
+                        self.arena[a:e].copy_(st[a - lo: e - lo], non_blocking=True)
+                        self.h2d_bytes += 4 * (e - a)
             for b in x["dev_up"]:
                 self.arena[b.off: b.off + b.n].copy_(b.tensor.detach().reshape(-1))
 
-    def download(self):
-        """Write every bound tensor (writeback=True) back into its original storage, in place.  Only the runs that hold
-        write-back mirrors cross PCIe (a pass that leaves the weights alone does not fetch them)."""
+    def download_begin(self):
+        """Enqueue the device-to-host copies of every write-back run (asynchronous; host work that does not read the results
+        can overlap them).  download_end() waits and writes the tensors."""
+        x = self._transfer_lists()
+        with torch.no_grad():
+            lo, st = x["lo"], self._staging
+            for a, e in x["d2h_runs"]:
+                st[a - lo: e - lo].copy_(self.arena[a:e], non_blocking=True)
+                self.d2h_bytes += 4 * (e - a)
+
+    def download_end(self):
         x = self._transfer_lists()
         with torch.no_grad():
             if x["d2h_runs"]:
-                lo, st = x["lo"], self._staging
-                for a, e in x["d2h_runs"]:
-                    st[a - lo: e - lo].copy_(self.arena[a:e], non_blocking=True)
-                    self.d2h_bytes += 4 * (e - a)
                 if self.arena.is_cuda:
                     torch.cuda.current_stream().synchronize()
                 dst, src = [], []
-                for b, v in zip(x["d2h_bounds"], x["d2h_src"]):
+                for b, v in (() if self._host_copy(x, "d2h", 1) else zip(x["d2h_bounds"], x["d2h_src"])):
                     t = b.tensor.detach()
                     if t.is_contiguous():
                         dst.append(t.view(-1)); src.append(v)
@@ -227,6 +285,12 @@ class Session:
                     torch._foreach_copy_(dst, src)
             for b in x["dev_down"]:
                 b.tensor.detach().copy_(self.arena[b.off: b.off + b.n].reshape(b.tensor.shape))
+
+    def download(self):
+        """Write every bound tensor (writeback=True) back into its original storage, in place.  Only the runs that hold
+        write-back mirrors cross PCIe (a pass that leaves the weights alone does not fetch them)."""
+        self.download_begin()
+        self.download_end()
 
     def view(self, off: int, n: int) -> torch.Tensor:
         self._ensure_room()

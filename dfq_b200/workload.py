@@ -312,8 +312,9 @@ class HostStackCalibrator:
         self.s_run = torch.cuda.Stream(device)
         self.s_out = torch.cuda.Stream(device)
 
-    def run(self, host_in: torch.Tensor, host_out: torch.Tensor):
-        """host_in/host_out: pinned fp32 tensors of n_chunks * chunk_floats elements."""
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor, copy_only: bool = False):
+        """host_in/host_out: pinned fp32 tensors of n_chunks * chunk_floats elements.  ``copy_only`` moves the same chunks
+        through the same three streams without launching the kernels (the transfer ceiling of the box, for bench.py)."""
         n = host_in.numel() // self.chunk_floats
         F, S = self.chunk_floats, self.n_slots
         loaded = [torch.cuda.Event() for _ in range(n)]
@@ -335,7 +336,8 @@ class HostStackCalibrator:
                 load(i + 1)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(loaded[i])
-                self.slots[i % S].run()                           # returns when the equalization result is back
+                if not copy_only:
+                    self.slots[i % S].run()                       # returns when the equalization result is back
                 computed[i].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(computed[i])

@@ -21,6 +21,7 @@
 #ifndef DFQ_B200_H_
 #define DFQ_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -265,6 +266,13 @@ int dfq_observer_update(float* running_min, float* running_max, const float* sta
 int dfq_observe_quant(const float* x, float* y, int64_t batch, int64_t per_sample, float* running_min, float* running_max,
                       float* stat_out2, int flags, float momentum, int num_bits, int symmetric, int div_mode, int prologue,
                       void* stream);
+
+/* HOST-side helper of the residency (no CUDA call): copies n segments between scattered host buffers and one contiguous
+ * staging image - what Session.upload()/download() do around their single H2D / D2H copy (the reference moves a model with
+ * one `.cuda()` / `.cpu()` per tensor: main_cls.py:70, dfq.py:145-151).  Segment i is ptr[i] (host address), bytes[i] long and
+ * lives at byte offset off[i] of `staging`.  dir 0: staging <- segments (gather), dir 1: segments <- staging (scatter).
+ * threads <= 0: min(8, hardware threads); never more than one thread per MB. */
+int dfq_host_copy_segments(void* staging, void* const* ptr, const size_t* bytes, const size_t* off, int n, int dir, int threads);
 
 /* BN-statistics matching loss of the distilled-data generation (ZeroQ/distill_data.py:171-196) on one
  * BatchNorm input x [n, c, hw] (contiguous):  loss2[0] = sum_{n,c} (bn_mean[c] - mean_hw x)^2 / c,

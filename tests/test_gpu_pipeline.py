@@ -182,6 +182,65 @@ def test_graph_calibration_matches_separate_calls_on_gpu():
             assert np.array_equal(ma.bias.detach().numpy(), mb.bias.detach().numpy())
 
 
+def test_native_host_staging_equals_the_tensor_library_path(monkeypatch):
+    """Session.upload()/download() gather and scatter the model with dfq_host_copy_segments (pipelined in parts with the
+    H2D copy): same arena image and same results as the per-tensor torch path, also when a parameter's .data was re-pointed
+    or made non-contiguous between two runs (the addresses are read per call; a non-contiguous tensor falls back)."""
+    from dfq_b200.calibrate import GraphCalibration
+    from dfq_b200 import engine as engine_mod
+    from dfq_b200.engine import Session
+    topo = workload.load_topology(os.path.join(GOLD, "topology_mobilenetv2.json"))
+    ga, ba, _ = workload.build_graph(topo, seed=33)
+    gb, bb, _ = workload.build_graph(topo, seed=33)
+    cal_a = GraphCalibration(ga, ba, TARG)
+    calls = []
+    orig = Session._host_copy
+
+    def spy(self, x, which, direction, i0=0, i1=None):
+        ok = orig(self, x, which, direction, i0, i1)
+        calls.append((which, ok))
+        return ok
+    monkeypatch.setattr(Session, "_host_copy", spy)
+    monkeypatch.setattr(engine_mod, "_UPLOAD_PARTS", 3)                      # staged in parts, each followed by its H2D copy
+    cal_a.upload()
+    assert calls and all(ok for _, ok in calls) and len(calls) == 3
+    image_native = cal_a.sess.arena.clone()
+    cal_a.run_device(equalize=True, correction=True)
+    cal_a.download()
+    assert ("d2h", True) in calls
+    monkeypatch.setattr(Session, "_host_copy", lambda self, *a, **k: False)  # the tensor-library path
+    cal_b = GraphCalibration(gb, bb, TARG)
+    cal_b.upload()
+    xa, xb = cal_a.sess._transfer_lists(), cal_b.sess._transfer_lists()
+    for (a, e) in xa["h2d_runs"]:
+        assert torch.equal(image_native[a:e], cal_b.sess.arena[a:e])
+    cal_b.run_device(equalize=True, correction=True)
+    cal_b.download()
+    for ma, mb in zip(ga.values(), gb.values()):
+        if type(ma) in TARG:
+            assert torch.equal(ma.weight, mb.weight) and torch.equal(ma.bias, mb.bias)
+        if hasattr(ma, "fake_bias") and not isinstance(ma, str):
+            assert torch.equal(ma.fake_bias, mb.fake_bias) and torch.equal(ma.fake_weight, mb.fake_weight)
+    for ra, rb in zip(cal_a.relations, cal_b.relations):
+        assert torch.equal(ra.S, rb.S)
+    # second residency of the SAME plan after the caller re-pointed one weight and made another one non-contiguous
+    monkeypatch.setattr(Session, "_host_copy", spy)
+    convs = [m for m in ga.values() if type(m) == nn.Conv2d and m.weight.dim() == 4 and m.weight.size(1) > 1]
+    convs[0].weight.data = convs[0].weight.data.clone()
+    w = convs[1].weight.data
+    convs[1].weight.data = w.permute(1, 0, 2, 3).contiguous().permute(1, 0, 2, 3)   # same values, non-contiguous
+    assert not convs[1].weight.is_contiguous()
+    expect_w0, expect_w1 = convs[0].weight.detach().clone(), convs[1].weight.detach().clone()
+    del calls[:]
+    cal_a.upload()
+    assert any(not ok for _, ok in calls)                                    # fell back for the non-contiguous part
+    la, lb = cal_a._layer[[k for k in ga if ga[k] is convs[0]][0]], cal_a._layer[[k for k in ga if ga[k] is convs[1]][0]]
+    for li, ew in ((la, expect_w0), (lb, expect_w1)):
+        l = cal_a.sess.layer(li)
+        n = l["rows"] * l["cols"] * l["kk"]
+        assert torch.equal(cal_a.sess.arena[l["w_off"]: l["w_off"] + n].cpu(), ew.contiguous().reshape(-1))
+
+
 def test_relations_in_arbitrary_order_use_the_per_relation_path():
     """A hand-written relation list that is NOT in forward chain order must still follow dfq.py's Gauss-Seidel order."""
     from dfq_b200 import dfq
