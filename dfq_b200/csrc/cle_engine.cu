@@ -97,6 +97,12 @@ struct CleCtl {
   unsigned long long tile_ns[48][8];  // per-tile timeline of block 0 in the first pass (DFQ_TRACE): consumer 0-3, producer 4-7
 };
 
+#ifdef DFQ_STEP_TRACE
+// debug build: per-CTA timeline of every step of sweep 2 (thread 0 of each CTA): 0 step start, 1 first tile (or END) seen,
+// 2 layer context ready, 3 first tile computed, 4 first tile handed back, 5 END seen, 6 fenced (about to enter the grid
+// barrier), 7 tiles consumed
+__device__ unsigned long long g_step_trace[8][512][8];
+#endif
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -178,6 +184,37 @@ struct StagePub { float cmn, cmx, s, inv; int valid; int pad[3]; };
 
 // The per-channel bookkeeping of dfq.py:62-70 + relation.py:20-24 + the derived column extrema, for ONE channel.
 // All loads are issued before the first store (the stores would otherwise fence the loads one global latency apart).
+// The per-channel operands of publish_row: only the row's own publisher ever writes them, so they may be requested together
+// with the row's inputs, one global-memory latency before they are needed.
+struct RowPub { float a0, b0, w0, w1, o0, o1; };
+__device__ __forceinline__ RowPub fetch_row_pub(const RowCtx& c, const DfqCleParams P, int o) {
+  RowPub q;
+  const bool acc = !P.apply_only && !c.first_sweep;
+  q.a0 = acc ? __ldcg(c.s_acc + o) : 1.f;
+  q.b0 = __ldcg(c.bias + o);
+  q.w0 = c.bnw ? __ldcg(c.bnw + o) : 0.f;
+  q.w1 = c.bnb ? __ldcg(c.bnb + o) : 0.f;
+  q.o0 = c.own_cmin_wr ? __ldcg(c.own_cmin_wr + o) : 0.f;
+  q.o1 = c.own_cmin_wr ? __ldcg(c.own_cmax_wr + o) : 0.f;
+  return q;
+}
+__device__ __forceinline__ void publish_row_with(const RowCtx& c, const DfqCleParams P, int o, float s, float inv, float cmn,
+                                                 float cmx, const RowPub& q) {
+  c.s_step[o] = s;
+  __stcg(c.inv_out + o, inv);
+  if (!P.apply_only) c.s_acc[o] = c.first_sweep ? s : __fmul_rn(q.a0, s);
+  __stcg(c.bias + o, __fmul_rn(q.b0, s));
+  if (c.bnw) __stcg(c.bnw + o, __fmul_rn(q.w0, s));
+  if (c.bnb) __stcg(c.bnb + o, __fmul_rn(q.w1, s));
+  if (c.cmin_wr) {  // derived column extrema of the second layer after its column scaling
+    __stcg(c.cmin_wr + o, __fmul_rn(cmn, inv));
+    __stcg(c.cmax_wr + o, __fmul_rn(cmx, inv));
+  }
+  if (c.own_cmin_wr) {  // depthwise middle layer: its single-row column is this row
+    __stcg(c.own_cmin_wr + o, __fmul_rn(q.o0, s));
+    __stcg(c.own_cmax_wr + o, __fmul_rn(q.o1, s));
+  }
+}
 __device__ __forceinline__ void publish_row(const RowCtx& c, const DfqCleParams P, int o, float s, float inv, float cmn, float cmx) {
   const bool acc = !P.apply_only && !c.first_sweep;
   const float a0 = acc ? __ldcg(c.s_acc + o) : 1.f;
@@ -374,6 +411,72 @@ __device__ __forceinline__ void cle_row_smem(const RowCtx& c, const DfqCleParams
   dacc += (double)dsum * inv_n;
 }
 
+// A SHORT row (<= 64 float4 / scalar items) handled by G = 1..16 lanes, 32 / G rows per warp side by side: the depthwise
+// 3x3 rows of a MobileNetV2 are 9 floats and its 1x1 expansion rows 24-160 - a whole warp per row left 23-31 lanes idle and
+// a warp walked through up to 73 rows of a tile one after the other (6-7 us per 18 KB tile; the step's critical path).
+// Same arithmetic per element and the same (exact) min / max as cle_row_smem; every lane of the warp executes the
+// shuffles, lanes of a group without a row (`valid` false) only skip the memory accesses.
+#ifndef DFQ_SUB_ITEMS
+#define DFQ_SUB_ITEMS 8      // work items a lane takes of a short row (4: twice the rows-in-flight steps, measured slower)
+#endif
+template <int MODE, bool HAS_OUT>
+__device__ __forceinline__ void cle_row_sub(const RowCtx& c, const DfqCleParams P, float* __restrict__ row, int o, int sub, int G,
+                                            bool valid, bool vec, const float* __restrict__ s_inv, double& dacc, const RowIn& in,
+                                            float* s_out, float* inv_out) {
+  const int n = c.row_len, kk = c.kk, n4 = n >> 2;
+  const float* inv = nullptr;
+  const float u = in.u;
+  if (MODE == IN_KK1 || MODE == IN_KK9) inv = s_inv;
+  else if (MODE == IN_GENERIC) inv = c.inv_in + (o / c.in_go) * c.in_gi;
+  float s = 1.f, dsum = 0.f;
+  if (HAS_OUT) {
+    float mn = DFQ_INF, mx = -DFQ_INF;
+    if (valid) {
+      if (vec) {
+        const float4* r4 = (const float4*)row;
+        for (int i4 = sub; i4 < n4; i4 += G) {
+          const float4 t = in_scale4<MODE>(r4[i4], i4 * 4, inv, u, kk);
+          mn = fminf(mn, fminf(fminf(t.x, t.y), fminf(t.z, t.w)));
+          mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+        }
+      } else {
+        for (int e = sub; e < n; e += G) {
+          const float t = in_scale1<MODE>(row[e], e, inv, u, kk);
+          mn = fminf(mn, t); mx = fmaxf(mx, t);
+        }
+      }
+    }
+    for (int off = G >> 1; off; off >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    float iv;
+    s = solve_row(P, in, mn, mx, &iv);
+    *s_out = s; *inv_out = iv;
+  }
+  if (valid) {
+    if (vec) {
+      float4* r4 = (float4*)row;
+      for (int i4 = sub; i4 < n4; i4 += G) {
+        const float4 v = r4[i4];
+        float4 t = in_scale4<MODE>(v, i4 * 4, inv, u, kk);
+        if (HAS_OUT) { t.x = __fmul_rn(t.x, s); t.y = __fmul_rn(t.y, s); t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s); }
+        r4[i4] = t;
+        dsum += fabsf(__fsub_rn(t.x, v.x)) + fabsf(__fsub_rn(t.y, v.y)) + fabsf(__fsub_rn(t.z, v.z)) + fabsf(__fsub_rn(t.w, v.w));
+      }
+    } else {
+      for (int e = sub; e < n; e += G) {
+        const float v = row[e];
+        float t = in_scale1<MODE>(v, e, inv, u, kk);
+        if (HAS_OUT) t = __fmul_rn(t, s);
+        row[e] = t;
+        dsum += fabsf(__fsub_rn(t, v));
+      }
+    }
+  }
+  dacc += (double)dsum * c.inv_n;
+}
+
 // A tile of whole rows in shared memory, rescaled in place.
 //   one row   : the whole team works on it; its global-memory inputs arrive in the stage mailbox and the bookkeeping is left
 //               to the producer warp (mailbox again)
@@ -398,13 +501,38 @@ __device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParam
   } else {
     const int row_len = c.row_len;
     const int mine = (nrows - warp + kWarps - 1) / kWarps;       // this warp's rows: warp, warp + kWarps, ...
+    const bool vec = ((row_len & 3) == 0);
+    const int items = vec ? (row_len >> 2) : row_len;            // float4 / scalar work items of one row
+    int G = 32;                                                  // lanes per row
+    if (items <= 64) { G = 1; while (G * DFQ_SUB_ITEMS < items) G <<= 1; }   // short rows: up to DFQ_SUB_ITEMS items per lane, 32 / G rows at once
     for (int base = 0; base < mine; base += 32) {
       const int il = base + lane;
       const int ol = row0 + warp + il * kWarps;
       RowIn mine_in; mine_in.cmn = mine_in.cmx = 0.f; mine_in.u = 1.f; mine_in.s_given = 1.f;
-      if (il < mine) mine_in = fetch_row_in(c, P, ol, MODE == IN_UNIFORM);
+      RowPub mine_pub; mine_pub.a0 = mine_pub.b0 = mine_pub.w0 = mine_pub.w1 = mine_pub.o0 = mine_pub.o1 = 0.f;
+      if (il < mine) {
+        mine_in = fetch_row_in(c, P, ol, MODE == IN_UNIFORM);
+        if (HAS_OUT) mine_pub = fetch_row_pub(c, P, ol);          // in flight together with the inputs
+      }
       float ks = 1.f, kinv = 1.f;
       const int nb = min(32, mine - base);
+      if (G < 32) {
+        const int R = 32 / G, sub = lane & (G - 1), grp = lane / G;
+        for (int j = 0; j < nb; j += R) {
+          const bool valid = (j + grp < nb);
+          const int jj = valid ? j + grp : nb - 1;                 // lanes without a row shadow the last one (no stores)
+          const int r = warp + (base + jj) * kWarps;
+          RowIn in;
+          in.cmn = __shfl_sync(0xffffffffu, mine_in.cmn, jj); in.cmx = __shfl_sync(0xffffffffu, mine_in.cmx, jj);
+          in.u = __shfl_sync(0xffffffffu, mine_in.u, jj); in.s_given = __shfl_sync(0xffffffffu, mine_in.s_given, jj);
+          float sv = 1.f, iv = 1.f;
+          cle_row_sub<MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, row0 + r, sub, G, valid, vec, s_inv, dacc, in, &sv, &iv);
+          // row j + g was solved by lane group g: its publisher is lane j + g
+          const int src = ((lane - j) * G) & 31;
+          const float ss = __shfl_sync(0xffffffffu, sv, src), ii = __shfl_sync(0xffffffffu, iv, src);
+          if (lane >= j && lane < j + R && lane < nb) { ks = ss; kinv = ii; }
+        }
+      } else
       for (int j = 0; j < nb; ++j) {
         const int r = warp + (base + j) * kWarps;
         RowIn in;
@@ -414,7 +542,7 @@ __device__ __forceinline__ void cle_tile_rows(const RowCtx& c, const DfqCleParam
         cle_row_smem<32, MODE, HAS_OUT>(c, P, buf + (size_t)r * row_len, row0 + r, lane, s_inv, red, parity, dacc, in, &sv, &iv);
         if (lane == j) { ks = sv; kinv = iv; }
       }
-      if (HAS_OUT && il < mine) publish_row(c, P, ol, ks, kinv, mine_in.cmn, mine_in.cmx);
+      if (HAS_OUT && il < mine) publish_row_with(c, P, ol, ks, kinv, mine_in.cmn, mine_in.cmx, mine_pub);
     }
   }
 }
@@ -530,7 +658,7 @@ struct PassIter {
         do { ++q; } while (q + 1 < q_end && ptr[q + 1] <= cur.t);
         q_lo = ptr[q]; q_hi = ptr[q + 1];
       }
-      if (q != q_live) {
+      if (G != nullptr && q != q_live) {       // (G == nullptr: a single group - it is iterating as long as the kernel runs)
         const int g = L[step_layers[q]].group;
         if (g != g_seen) { g_done = *((volatile const int*)&G[g].done); g_seen = g; }   // flags only change between sweeps
         if (g_done) { cur.seek(q_hi); continue; }
@@ -609,11 +737,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 //   lane 1  per-channel bookkeeping of tile m (publish_row: S, 1/s, bias, BN vectors, derived column extrema)
 //   lane 2  prefetch of the new tile's column extrema into its mailbox
 // `scan`: the initial column scan -- tiles are only loaded, no mailbox traffic.
+// End of a step for the producer warp: its bulk stores have reached global memory, its bookkeeping stores are fenced.
+__device__ __forceinline__ void ws_drain() {
+  if ((threadIdx.x & 31) == 0) {
+    bulk_wait_all();
+    fence_proxy_async_all();
+  }
+  __threadfence();                  // lane 1's bookkeeping stores, before the grid barrier
+  __syncwarp();
+}
+
+// `ahead`: tiles of this step that ws_issue_ahead() already put into the ring (pit stands behind them).  `drain` = false:
+// the caller issues the next step's first loads while this step's stores are still on their way, then calls ws_drain().
 __device__ __noinline__ void ws_produce(float* arena, const DfqLayer* L, const DfqRelation* R, PassIter pit, WsPipe& ws,
-                           unsigned long long& count, const DfqCleParams P, int sweep, CleCtl* ctl, bool tr, bool scan) {
+                           unsigned long long& count, const DfqCleParams P, int sweep, CleCtl* ctl, bool tr, bool scan,
+                           int ahead = 0, bool drain = true) {
   const int lane = threadIdx.x & 31;
   const unsigned long long count0 = count;
-  unsigned long long n = count, m = count;     // next tile to issue / to retire (uniform across the warp)
+  unsigned long long n = count + (unsigned long long)ahead, m = count;     // next tile to issue / to retire (uniform across the warp)
   RowCtx ctx;                                  // lane 1: layer being retired; lane 2: layer being issued
   int li = -1;
   int end_pending = kTeams;                    // the TK_END sentinels go last, one per consumer team
@@ -674,13 +815,40 @@ __device__ __noinline__ void ws_produce(float* arena, const DfqLayer* L, const D
     }
     __syncwarp();
   }
-  if (lane == 0) {
-    bulk_wait_all();
-    fence_proxy_async_all();
-  }
-  __threadfence();                  // lane 1's bookkeeping stores, before the grid barrier
-  __syncwarp();
   count = n;
+  if (drain) ws_drain();
+}
+
+// Before the grid barrier that ends a step: start loading the first tiles of the NEXT step (the ring is empty at that
+// point).  A layer's weights are only ever written in its own step, by the CTA that owns the tile (the tile -> CTA map is
+// static), so these loads need nothing from the barrier; what does depend on it - 1/s of the in-relation, the column
+// extrema - is read by the consumers behind it.  The mailbox of such a tile stays invalid: the consumers fetch and publish
+// the row themselves.  On a MobileNetV2 the first tile used to arrive 2.3-2.6 us after the barrier (iterator start + L2 ->
+// shared memory), of ~12 us per step.  Returns the number of tiles issued (sequence numbers count .. count + a - 1).
+__device__ __noinline__ int ws_issue_ahead(float* arena, PassIter& pit, WsPipe& ws, unsigned long long count) {
+  const int lane = threadIdx.x & 31;
+  int a = 0;
+  for (; a < kCleStages && pit.valid(); ++a) {
+    TileDesc d;
+    pit.fill(d, arena);
+    pit.next();
+    const int si = (int)((count + (unsigned long long)a) % kCleStages);
+    if (lane == 0) {
+      *ws.desc(si) = d;
+      if (d.kind == TK_BULK) {
+        mbar_expect_tx(ws.full(si), (uint32_t)d.floats * 4u);
+        bulk_g2s(ws.stage(si), d.gptr, (uint32_t)d.floats * 4u, ws.full(si));
+      }
+    }
+    if (lane == 2) {
+      StagePub pb; pb.valid = 0; pb.cmn = pb.cmx = pb.s = pb.inv = 0.f;
+      *ws.pub(si) = pb;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ws.full(si));
+  }
+  __syncwarp();
+  return a;
 }
 
 __global__ void __launch_bounds__(kCtaThreads, kCleCtas)
@@ -806,13 +974,27 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
   grid.sync();
   mark();
 
+  // single model (one convergence group): the producer warp runs one step ahead with its loads (ws_issue_ahead)
+  const bool run_ahead = (nG == 1);
+  PassIter it_ahead;
+  int ahead = -1;                    // < 0: the iterator of the coming step has not been started
   for (int sweep = 0;; ++sweep) {
     const int slot = sweep % 3;
     for (int p = 0; p < n_steps; ++p) {
       if (producer) {
-        PassIter it;
-        it.start(pass_ptr, step_layers, L, G, step_ptr[p], step_ptr[p + 1]);
-        ws_produce(arena, L, R, it, ws, count, P, sweep, ctl, blockIdx.x == 0 && sweep == 0 && p == 0, false);
+        if (ahead < 0) {
+          it_ahead.start(pass_ptr, step_layers, L, nG == 1 ? nullptr : G, step_ptr[p], step_ptr[p + 1]);
+          ahead = 0;
+        }
+        ws_produce(arena, L, R, it_ahead, ws, count, P, sweep, ctl, blockIdx.x == 0 && sweep == 0 && p == 0, false, ahead,
+                   !run_ahead);
+        ahead = -1;
+        if (run_ahead) {
+          const int pn = (p + 1 < n_steps) ? p + 1 : 0;      // (a sweep that turns out to be the last one: drained at exit)
+          it_ahead.start(pass_ptr, step_layers, L, nullptr, step_ptr[pn], step_ptr[pn + 1]);
+          ahead = ws_issue_ahead(arena, it_ahead, ws, count);
+          ws_drain();
+        }
       } else {
         double dacc = 0.0;
         int cur_g = -1;
@@ -851,11 +1033,20 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
 #else
 #define DFQ_TT(i) do { } while (0)
 #endif
+#ifdef DFQ_STEP_TRACE
+        const bool st_tr = (sweep == 2 && threadIdx.x == 0 && p < 8 && blockIdx.x < 512);
+        int st_n = 0;
+#define DFQ_ST(i) do { if (st_tr && st_n == 0) g_step_trace[p][blockIdx.x][i] = gtimer(); } while (0)
+        if (st_tr) { g_step_trace[p][blockIdx.x][0] = gtimer(); for (int i = 1; i < 8; ++i) g_step_trace[p][blockIdx.x][i] = 0; }
+#else
+#define DFQ_ST(i) do { } while (0)
+#endif
         for (count = my_first(count);; count += kTeams) {
           const int sidx = (int)(count % kCleStages);
           DFQ_TT(0);
           mbar_wait(ws.full(sidx), (uint32_t)((count / kCleStages) & 1));
           DFQ_TT(1);
+          DFQ_ST(1);
           // the descriptor stays in shared memory (valid until `done` is arrived): the loop is short of registers
           const volatile TileDesc& d = *ws.desc(sidx);
           if (d.kind == TK_END) { mbar_arrive(ws.done(sidx)); count += 1 + d.nrows; break; }
@@ -878,8 +1069,17 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
             else if (sctx.inv_cached && sctx.kk == 9) in_mode = IN_KK9;
             else in_mode = IN_GENERIC;
             if (in_mode == IN_KK1 || in_mode == IN_KK9) {
-              for (int j = ctid(); j < sctx.cols; j += kThreads) s_inv[j] = __ldcg(sctx.inv_in + j);
-              if (ctid() == 0) s_inv[sctx.cols] = 1.f;
+              // four loads in flight per thread: one L2 latency per 4 x kThreads columns instead of one per kThreads
+              const int ncol = sctx.cols;
+              const float* src = sctx.inv_in;
+              for (int j0 = ctid(); j0 < ncol; j0 += 4 * kThreads) {
+                float t[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[k] = (j0 + k * kThreads < ncol) ? __ldcg(src + j0 + k * kThreads) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (j0 + k * kThreads < ncol) s_inv[j0 + k * kThreads] = t[k];
+              }
+              if (ctid() == 0) s_inv[ncol] = 1.f;
               cbar();
             }
             rs_flush();
@@ -897,6 +1097,7 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
               cbar();
             }
           }
+          DFQ_ST(2);
           // the re-scanned successor's next-sweep buffer is reset HERE, one step (= one grid barrier) before its pass fills it
           if (d.row0 == 0 && sctx.has_out) {
             const DfqRelation ro = R[L[cur_li].rel_out];
@@ -914,7 +1115,9 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
           } else {
             StagePub* pub = ws.pub(sidx);
             cle_tile_smem(c, P, in_mode, buf, d.row0, d.nrows, s_inv, red, parity, dacc, pub->valid ? pub : nullptr);
+            DFQ_ST(3);
             if (rs_li >= 0 || d.kind != TK_BULK) cbar();      // every row of the tile is final in the stage
+            DFQ_ST(7);
             if (rs_li >= 0)
               colscan_tile_ool<false>(buf, ctid(), d.row0, d.nrows, c.cols, c.kk, rsx.go, rsx.gi, rsx.single, rsx.own, rsx.smem,
                                             rs_min, rs_max, rsx.dmin, rsx.dmax);
@@ -923,15 +1126,26 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
             mbar_arrive(ws.done(sidx));         // hand the tile back to the producer
           }
           DFQ_TT(2);
+          DFQ_ST(4);
+#ifdef DFQ_STEP_TRACE
+          st_n++;
+#endif
 #ifdef DFQ_TILE_TRACE
           trn++;
 #endif
         }
 #undef DFQ_TT
+#ifdef DFQ_STEP_TRACE
+        if (st_tr) g_step_trace[p][blockIdx.x][5] = gtimer();
+#endif
         rs_flush();
         flush();
         fence_proxy_async_all();   // this pass's plain row stores -> the next pass's bulk loads (async proxy)
         __threadfence();
+#ifdef DFQ_STEP_TRACE
+        if (st_tr) g_step_trace[p][blockIdx.x][6] = gtimer();
+#endif
+#undef DFQ_ST
       }
       grid.sync();
       mark();
@@ -985,6 +1199,12 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
     grid.sync();
     if (*((volatile int*)&ctl->active[n & 1]) == 0) break;
   }
+  // loads issued ahead for a step that never comes must have landed before the CTA's shared memory goes away
+  if (producer && ahead > 0 && (threadIdx.x & 31) == 0)
+    for (int a = 0; a < ahead; ++a) {
+      const unsigned long long c = count + (unsigned long long)a;
+      mbar_wait(ws.full((int)(c % kCleStages)), (uint32_t)((c / kCleStages) & 1));
+    }
 }
 
 
@@ -1417,6 +1637,31 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
     fprintf(stderr, "[dfq_cle_run] grid %d (%d CTAs/SM) sweeps %d; phase ms:", grid, per_sm, result->n_sweeps);
     for (int i = 1; i < 32 && h.t_ns[i]; ++i) fprintf(stderr, " %.3f", (h.t_ns[i] - h.t_ns[i - 1]) * 1e-6);
     fprintf(stderr, "\n");
+#ifdef DFQ_STEP_TRACE
+    {
+      static unsigned long long hs[8][512][8];
+      cudaMemcpyFromSymbol(hs, g_step_trace, sizeof(hs));
+      const int nb = std::min(grid, 512);
+      for (int p = 0; p < std::min(n_steps, 8); ++p) {
+        int last = 0, busy = 0; unsigned long long first_start = ~0ull;
+        std::vector<unsigned long long> arr;
+        for (int b = 0; b < nb; ++b) {
+          if (hs[p][b][6] > hs[p][last][6]) last = b;
+          if (hs[p][b][3]) busy++;
+          first_start = std::min(first_start, hs[p][b][0]);
+          arr.push_back(hs[p][b][6]);
+        }
+        std::sort(arr.begin(), arr.end());
+        const unsigned long long* t = hs[p][last];
+        auto us = [&](unsigned long long v) { return v ? (double)(v - first_start) * 1e-3 : -1.0; };
+        unsigned long long next_start = ~0ull;
+        if (p + 1 < std::min(n_steps, 8)) for (int b = 0; b < nb; ++b) next_start = std::min(next_start, hs[p + 1][b][0]);
+        fprintf(stderr, "[step %d] busy CTAs %d/%d; last CTA %d: start %.2f firsttile %.2f ctx %.2f computed %.2f barrier %.2f handedback %.2f end %.2f fenced %.2f | median fenced %.2f | next step starts %.2f\n",
+                p, busy, nb, last, us(t[0]), us(t[1]), us(t[2]), us(t[3]), us(t[7]), us(t[4]), us(t[5]), us(t[6]), us(arr[arr.size() / 2]),
+                next_start != ~0ull ? us(next_start) : -1.0);
+      }
+    }
+#endif
     if (getenv("DFQ_TRACE_TILES")) {
       const unsigned long long t0 = h.tile_ns[0][1];
       fprintf(stderr, "tile: C.wait C.ready C.done C.arrived | P.retire P.stored P.loadissued P.fullarrive  (us since first load)\n");

@@ -16,6 +16,17 @@ template <int NT, bool GLOBAL>
 __device__ __forceinline__ void colscan_tile(const float* __restrict__ buf, int tid, int row0, int nrows, int J, int kk, int go,
                                              int gi, bool single_group, bool own, bool use_smem, float* smin, float* smax,
                                              float* dmin, float* dmax) {
+  if (!GLOBAL && kk == 1 && single_group && use_smem) {
+    // 1x1 rows of an ungrouped layer: a thread per COLUMN walks down the tile's rows (conflict-free, no division, no atomics).
+    // Column j belongs to thread j % NT in every tile of the layer, and the scratch is private to the NT threads between two
+    // flushes: plain read-modify-write.
+    for (int j = tid; j < J; j += NT) {
+      float mn = buf[j], mx = mn;
+      for (int r = 1; r < nrows; ++r) { const float v = buf[(size_t)r * J + j]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+      smin[j] = fminf(smin[j], mn); smax[j] = fmaxf(smax[j], mx);
+    }
+    return;
+  }
   const int items = nrows * J;
   for (int idx = tid; idx < items; idx += NT) {
     const float* p = buf + (size_t)idx * kk;
