@@ -92,11 +92,11 @@ class ClockSampler(threading.Thread):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the equalization kernel (k_cle_stack) from the committed `ncu --set full`
-# capture (profiles/r2_cle_stack_v1.md: 19.350 GB read + 19.300 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The
+# capture (profiles/r2_cle_stack_v2.md: 19.346 GB read + 19.292 GB written at 1024 pairs, 2 sweeps; algorithmic 38.655 GB).  The
 # kernel's traffic is linear in the number of pairs (every block is identical), so the figure is scaled to the benched size;
 # None for other sweep counts.  (k_cle_engine, round 1: 38.809 GB, profiles/r1_ncu_full_1024layers.md.)
-NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.650e9
-NCU_TRAFFIC_SOURCE = "ncu --set full capture of k_cle_stack at 1024 pairs (profiles/r2_cle_stack_v1.md), scaled linearly to the benched pairs"
+NCU_TRAFFIC_1024_PAIRS_2_SWEEPS = 38.638e9
+NCU_TRAFFIC_SOURCE = "ncu --set full capture of k_cle_stack at 1024 pairs (profiles/r2_cle_stack_v2.md), scaled linearly to the benched pairs"
 
 
 def ncu_traffic(layers, sweeps):
