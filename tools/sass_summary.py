@@ -40,6 +40,6 @@ log = os.path.join(ROOT, "dfq_b200", "build.log")
 if os.path.exists(log):
     print("\nptxas (`dfq_b200/build.log`): registers / spill bytes per kernel\n\n| kernel | registers | spill stores (B) | spill loads (B) |\n|---|---|---|---|")
     text = open(log).read()
-    for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'.*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", text):
+    for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\n[^\n]*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n[^\n]*Used (\d+) registers", text):
         nm = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0].replace("dfq::", "")
         print("| `%s` | %s | %s | %s |" % (nm, m.group(5), m.group(3), m.group(4)))
