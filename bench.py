@@ -278,7 +278,17 @@ def mobilenetv2_latency(dev, reps=5):
     eps0 = [getattr(m, "eps", None) for m in modules]
 
     def restore():
-        """Undo a calibration in place (parameters stay the same objects the plan is bound to)."""
+        """Undo a calibration in place (parameters stay the same objects the plan is bound to).  Single-threaded: the tensor
+        library's OpenMP workers keep spinning on every allowed CPU for a while after a parallel copy, and this harness step
+        ends right where the timed region begins (the rank is bound to one NUMA node's CPUs)."""
+        nt = torch.get_num_threads()
+        torch.set_num_threads(1)
+        try:
+            _restore()
+        finally:
+            torch.set_num_threads(nt)
+
+    def _restore():
         with torch.no_grad():
             for m, sd, e in zip(modules, backup, eps0):
                 if isinstance(m, (nn.Conv2d, nn.Linear)):
