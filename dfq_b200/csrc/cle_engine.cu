@@ -1049,7 +1049,8 @@ k_cle_engine(float* arena, const DfqLayer* __restrict__ gL, int nL, const DfqRel
           DFQ_ST(1);
           // the descriptor stays in shared memory (valid until `done` is arrived): the loop is short of registers
           const volatile TileDesc& d = *ws.desc(sidx);
-          if (d.kind == TK_END) { mbar_arrive(ws.done(sidx)); count += 1 + d.nrows; break; }
+          // (the descriptor is read BEFORE the arrival: the producer may refill this stage for the next step right away)
+          if (d.kind == TK_END) { const int rest = d.nrows; mbar_arrive(ws.done(sidx)); count += 1 + (unsigned)rest; break; }
           float* buf = ws.stage(sidx);
           if (d.kind == TK_PLAIN) {            // a tile the TMA unit cannot move: cooperative fetch
             for (int i = ctid(); i < d.floats; i += kThreads) buf[i] = ldg_stream1(d.gptr + i);
