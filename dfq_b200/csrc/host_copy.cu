@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
@@ -71,9 +72,20 @@ struct Pool {
   }
 };
 
-Pool* pool() {
-  static Pool* p = new Pool();     // never destroyed: parked helpers may outlive static destruction at process exit
-  return p;
+Pool* g_pool = nullptr;
+std::mutex* g_one_job = nullptr;     // one job at a time through the shared pool
+
+// A forked child inherits the pool's memory but none of its threads (and possibly a locked mutex): start over there.
+void forget_pool_in_child() { g_pool = nullptr; g_one_job = nullptr; }
+
+void ensure_globals() {
+  static std::once_flag once;
+  std::call_once(once, [] { pthread_atfork(nullptr, nullptr, forget_pool_in_child); });
+  static std::mutex init_m;
+  std::lock_guard<std::mutex> g(init_m);
+  // never destroyed: parked helpers may outlive static destruction at process exit
+  if (!g_one_job) g_one_job = new std::mutex();
+  if (!g_pool) g_pool = new Pool();
 }
 
 }  // namespace
@@ -96,9 +108,9 @@ extern "C" int dfq_host_copy_segments(void* staging, void* const* ptr, const siz
     copy_range(j, 0, j.total);
     return DFQ_OK;
   }
-  Pool& p = *pool();
-  static std::mutex one_job;                            // one job at a time through the shared pool
-  std::lock_guard<std::mutex> serial(one_job);
+  ensure_globals();
+  std::lock_guard<std::mutex> serial(*g_one_job);
+  Pool& p = *g_pool;
   std::unique_lock<std::mutex> lk(p.m);
   try { p.ensure(T - 1); } catch (...) { }              // no helper threads available: this thread does every chunk
   p.job = j; p.next = 0; p.nchunks = nchunks; p.done = 0;

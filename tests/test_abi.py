@@ -103,3 +103,32 @@ def test_host_copy_segments_gathers_and_scatters_ragged_tensors():
     assert lib.dfq_host_copy_segments(None, None, None, None, 3, 0, 0) == _lib.load().dfq_host_copy_segments(None, None, None, None, 3, 1, 0) != 0
     assert lib.dfq_host_copy_segments(C.c_void_p(staging.ctypes.data), _lib.table_ptr(ptrs), _lib.table_ptr(nbytes),
                                       _lib.table_ptr(offa), len(sizes), 2, 0) != 0
+
+
+def test_host_copy_pool_survives_a_fork():
+    """The helper threads do not exist in a forked child (DataLoader workers fork): the child starts its own pool."""
+    import ctypes as C
+    from dfq_b200 import _lib
+    lib = _lib.load()
+
+    def roundtrip():
+        src = np.arange(3_000_000, dtype=np.float32)
+        staging = np.zeros(src.size + 4, dtype=np.float32)
+        ptrs = np.array([src.ctypes.data], dtype=np.uint64)
+        nbytes = np.array([4 * src.size], dtype=np.uint64)
+        offs = np.array([16], dtype=np.uint64)
+        rc = lib.dfq_host_copy_segments(C.c_void_p(staging.ctypes.data), _lib.table_ptr(ptrs), _lib.table_ptr(nbytes),
+                                        _lib.table_ptr(offs), 1, 0, 4)
+        return rc == 0 and np.array_equal(staging[4:], src)
+
+    assert roundtrip()                 # the parent's pool exists now
+    pid = os.fork()
+    if pid == 0:
+        ok = False
+        try:
+            ok = roundtrip()
+        finally:
+            os._exit(0 if ok else 1)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    assert roundtrip()
