@@ -42,8 +42,8 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--layers", type=int, default=4096, help="Conv/BN pairs in the synthetic stack per GPU")
     p.add_argument("--e2e-layers", type=int, default=512, help="pairs moved host->device->host per e2e step")
-    p.add_argument("--e2e-chunk", type=int, default=32, help="pairs per pipelined chunk of the e2e arm")
-    p.add_argument("--e2e-slots", type=int, default=4, help="arena slots of the e2e pipeline")
+    p.add_argument("--e2e-chunk", type=int, default=16, help="pairs per pipelined chunk of the e2e arm (measured: 32 pairs / 4 slots 4.93 k pairs/s, 16 / 6 5.05 k)")
+    p.add_argument("--e2e-slots", type=int, default=6, help="arena slots of the e2e pipeline")
     p.add_argument("--cpu-layers", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--quantize", action="store_true", help="also fake-quantize weights/biases (8 bit) inside the step")
@@ -507,7 +507,7 @@ def run_b200(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         from dfq_b200.workload import HostStackCalibrator
-        chunk_blocks = max(1, args.e2e_chunk // 2)                # 32 layer pairs = 302 MB per chunk
+        chunk_blocks = max(1, args.e2e_chunk // 2)                # 16 layer pairs = 151 MB per chunk
         # 2 x 4.8 GB of page-locked memory per rank at 512 pairs, allocated on the rank's own NUMA node (bind_to_gpu_numa_node)
         e2e_pairs = args.e2e_layers
         del pristine

@@ -1535,11 +1535,14 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
       DFQ_CUDA(cudaLaunchCooperativeKernel((void*)k_cle_stack, dim3(grid_s), dim3(kBcThreads), args, dyn_s, st));
       CleCtl h;
       std::vector<GroupState> hg(n_groups);
-      DFQ_CUDA(cudaMemcpyAsync(&h, dctl, sizeof(CleCtl), cudaMemcpyDeviceToHost, st));
-      DFQ_CUDA(cudaMemcpyAsync(hg.data(), dG, sizeof(GroupState) * n_groups, cudaMemcpyDeviceToHost, st));
+      ReadBack rb;
+      rb.add(&h, dctl, sizeof(CleCtl));
+      rb.add(hg.data(), dG, sizeof(GroupState) * n_groups);
+      { const int rrc = rb.enqueue(st); if (rrc) return rrc; }
       tp.release(st);
       free_async(dctl, st); free_async(dG, st);
       DFQ_CUDA(cudaStreamSynchronize(st));
+      rb.finish();
       result->n_sweeps = 0; result->converged = 1;
       for (int g = 0; g < n_groups; ++g) {
         result->n_sweeps = std::max(result->n_sweeps, hg[g].n_sweeps);
@@ -1620,11 +1623,14 @@ extern "C" int dfq_cle_run(float* arena, int64_t arena_floats, const DfqLayer* l
   h_launch = ms_since(h0);
   CleCtl h;
   std::vector<GroupState> hg(n_groups);
-  DFQ_CUDA(cudaMemcpyAsync(&h, dctl, sizeof(CleCtl), cudaMemcpyDeviceToHost, st));
-  DFQ_CUDA(cudaMemcpyAsync(hg.data(), dG, sizeof(GroupState) * n_groups, cudaMemcpyDeviceToHost, st));
+  ReadBack rb;
+  rb.add(&h, dctl, sizeof(CleCtl));
+  rb.add(hg.data(), dG, sizeof(GroupState) * n_groups);
+  { const int rrc = rb.enqueue(st); if (rrc) return rrc; }
   tp.release(st);
   free_async(dctl, st); free_async(dG, st);
   DFQ_CUDA(cudaStreamSynchronize(st));
+  rb.finish();
   result->n_sweeps = 0;
   result->converged = 1;
   for (int g = 0; g < n_groups; ++g) {

@@ -44,9 +44,12 @@ inline void free_async(void* p, cudaStream_t st) {
 
 int sm_count();
 
-// All descriptor tables of one call are packed into a page-locked staging slot (ring of 4, reused after the copy that
-// read it has completed) and moved with ONE truly asynchronous H2D copy into ONE stream-ordered device allocation.
-// (Copies from pageable memory block the host until the stream reaches them and stall the GPU between launches.)
+// All descriptor tables of one call are packed into a MAPPED page-locked staging slot (ring of 4, reused after the copy
+// that read it has completed) and moved into ONE stream-ordered device allocation by a small KERNEL that reads the slot over
+// PCIe - not by cudaMemcpyAsync: a copy of a few KB queues on the H2D copy engine behind whatever bulk copy is running, and
+// in the pipelined host-streaming use (300 MB chunks each way) every launch's tables waited ~6 ms for the NEXT chunk's
+// upload to finish, which in turn kept the host from enqueueing the chunk after that (bench.py e2e: 41.7 of 47 GB/s).
+// DFQ_TABLES_COPY_ENGINE=1 restores the memcpy path.
 struct TablePack {
   struct Item { const void* src; size_t bytes; size_t off; };
   Item items[12];
@@ -64,6 +67,23 @@ struct TablePack {
   T* ptr(int i) const { return (T*)(dev + items[i].off); }
   int upload(cudaStream_t st);                   // 0 or an error code (message set)
   void release(cudaStream_t st) { if (dev) cudaFreeAsync(dev, st); dev = nullptr; }
+};
+
+// Small device -> host read-back that stays off the copy engines, like the descriptor upload above: a kernel stores the
+// blocks into mapped page-locked memory; the caller synchronizes the stream and copies them out.
+struct ReadBack {
+  struct Item { void* host; const void* dev; size_t bytes; size_t off; };
+  Item items[4];
+  int n = 0;
+  size_t total = 0;
+  int slot = -1;
+  unsigned char* mapped = nullptr;
+  void add(void* host, const void* dev, size_t bytes) {
+    items[n++] = Item{host, dev, bytes, total};
+    total += (bytes + 255) & ~(size_t)255;
+  }
+  int enqueue(cudaStream_t st);   // 0 or an error code (message set)
+  void finish();                  // after the stream has been synchronized
 };
 
 // ------------------------------------------------------------------------------------------

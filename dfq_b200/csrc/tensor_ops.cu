@@ -32,12 +32,73 @@ int sm_count() {
 }
 
 namespace {
-struct Slot { unsigned char* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+struct Slot { unsigned char* host = nullptr; unsigned char* dev = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
 Slot g_slots[4];
 int g_next_slot = 0;
 std::mutex g_slot_mu;
 bool g_pool_tuned = false;
 }  // namespace
+
+// word-wise copy between device memory and mapped page-locked host memory (either direction), a few KB to a few hundred KB
+__global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t nwords) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int launch_copy_words(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const size_t nwords = bytes / 4;
+  if (nwords == 0) return 0;
+  const int blocks = (int)std::min<size_t>(64, (nwords + 255) / 256);
+  k_copy_words<<<blocks, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, nwords);
+  DFQ_CUDA(cudaGetLastError());
+  return 0;
+}
+static bool tables_via_copy_engine() {
+  static const bool v = [] { const char* e = getenv("DFQ_TABLES_COPY_ENGINE"); return e && atoi(e) != 0; }();
+  return v;
+}
+
+namespace {
+struct RbSlot { unsigned char* host = nullptr; unsigned char* dev = nullptr; size_t cap = 0; bool busy = false; };
+RbSlot g_rb[4];
+std::mutex g_rb_mu;
+}  // namespace
+
+int ReadBack::enqueue(cudaStream_t st) {
+  if (tables_via_copy_engine()) {
+    for (int i = 0; i < n; ++i) DFQ_CUDA(cudaMemcpyAsync(items[i].host, items[i].dev, items[i].bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_rb_mu);
+    for (int i = 0; i < 4 && slot < 0; ++i) if (!g_rb[i].busy) { slot = i; g_rb[i].busy = true; }
+  }
+  if (slot < 0) {   // more than four read-backs in flight (concurrent host threads): the copy engine will do
+    for (int i = 0; i < n; ++i) DFQ_CUDA(cudaMemcpyAsync(items[i].host, items[i].dev, items[i].bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  RbSlot& sl = g_rb[slot];
+  if (sl.cap < total) {
+    if (sl.host) cudaFreeHost(sl.host);
+    sl.host = nullptr; sl.cap = 0;
+    const size_t cap = std::max<size_t>(total, 256 << 10);
+    DFQ_CUDA(cudaHostAlloc((void**)&sl.host, cap, cudaHostAllocMapped));
+    DFQ_CUDA(cudaHostGetDevicePointer((void**)&sl.dev, sl.host, 0));
+    sl.cap = cap;
+  }
+  mapped = sl.host;
+  for (int i = 0; i < n; ++i) {
+    const int rc = launch_copy_words(sl.dev + items[i].off, items[i].dev, items[i].bytes, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+void ReadBack::finish() {
+  if (slot < 0) return;
+  for (int i = 0; i < n; ++i) memcpy(items[i].host, mapped + items[i].off, items[i].bytes);
+  std::lock_guard<std::mutex> lk(g_rb_mu);
+  g_rb[slot].busy = false;
+  slot = -1;
+}
 
 int TablePack::upload(cudaStream_t st) {
   dev = nullptr;
@@ -57,13 +118,19 @@ int TablePack::upload(cudaStream_t st) {
   if (sl.cap < total) {
     if (sl.host) cudaFreeHost(sl.host);
     sl.cap = std::max<size_t>(total, 1 << 20);
-    DFQ_CUDA(cudaHostAlloc((void**)&sl.host, sl.cap, cudaHostAllocDefault));
+    DFQ_CUDA(cudaHostAlloc((void**)&sl.host, sl.cap, cudaHostAllocMapped));
+    DFQ_CUDA(cudaHostGetDevicePointer((void**)&sl.dev, sl.host, 0));
   }
   if (!sl.ev) DFQ_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
   for (int i = 0; i < n; ++i)
     if (items[i].bytes) memcpy(sl.host + items[i].off, items[i].src, items[i].bytes);
   DFQ_CUDA(cudaMallocAsync((void**)&dev, total, st));
-  DFQ_CUDA(cudaMemcpyAsync(dev, sl.host, total, cudaMemcpyHostToDevice, st));
+  if (tables_via_copy_engine()) {
+    DFQ_CUDA(cudaMemcpyAsync(dev, sl.host, total, cudaMemcpyHostToDevice, st));
+  } else {
+    const int rc = launch_copy_words(dev, sl.dev, total, st);
+    if (rc) return rc;
+  }
   DFQ_CUDA(cudaEventRecord(sl.ev, st));
   sl.used = true;
   return 0;
