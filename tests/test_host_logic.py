@@ -293,3 +293,49 @@ def test_export_round_trip_cpu(tmp_path, monkeypatch):
     import test_gpu_pipeline as T
     fakelib.install(monkeypatch)
     assert T.export_round_trip(tmp_path) == 42
+
+
+def test_native_host_staging_through_a_cpu_session(monkeypatch):
+    """Session.upload()/download() with the REAL dfq_host_copy_segments (the library loads without a GPU) attached to the
+    oracle-backed fake: parts planning, the gather per part, the split download and the scatter give the same calibrated model
+    as the per-tensor torch path - the CPU twin of test_gpu_pipeline.py::test_native_host_staging_equals_the_tensor_library_path."""
+    import ctypes as C
+    from dfq_b200 import _build, _lib, engine
+    from dfq_b200.calibrate import GraphCalibration
+    _build.build()
+    real = C.CDLL(_lib.LIB_PATH)
+    fn = real.dfq_host_copy_segments
+    fn.argtypes = _lib.SIGNATURES["dfq_host_copy_segments"]
+    fn.restype = C.c_int
+    topo = workload.load_topology(os.path.join(GOLD, "topology_mobilenetv2.json"))
+    targ = [nn.Conv2d, nn.Linear]
+    ga, ba, _ = workload.build_graph(topo, seed=4)
+    gb, bb, _ = workload.build_graph(topo, seed=4)
+    fake = fakelib.install(monkeypatch)
+    cal_b = GraphCalibration(gb, bb, targ)                 # tensor-library path (the fake has no host-copy entry)
+    cal_b.run(equalize=True, correction=True)
+    calls = []
+
+    def spy(*a):
+        calls.append(int(a[5]))                            # direction
+        return fn(*a)
+    fake.dfq_host_copy_segments = spy
+    monkeypatch.setattr(engine, "_UPLOAD_PARTS", 3)
+    cal_a = GraphCalibration(ga, ba, targ)
+    parts = cal_a.sess._upload_parts(cal_a.sess._transfer_lists())
+    up = cal_a.sess._transfer_lists()["h2d_bounds"]
+    assert 2 <= len(parts) <= 3 and parts[0][0] == 0 and parts[-1][1] == len(up)
+    assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))                       # contiguous, nothing skipped
+    for i0, i1, runs in parts:                                                         # every mirror lies inside a run of its part
+        for b in up[i0:i1]:
+            assert any(a <= b.off and b.off + b.n <= e for a, e in runs)
+    cal_a.run(equalize=True, correction=True)
+    assert calls.count(0) == len(parts) and calls.count(1) == 1
+    for ma, mb in zip(ga.values(), gb.values()):
+        if type(ma) in targ:
+            assert torch.equal(ma.weight, mb.weight) and torch.equal(ma.bias, mb.bias)
+        if isinstance(ma, nn.BatchNorm2d) and hasattr(ma, "fake_bias"):
+            assert torch.equal(ma.fake_bias, mb.fake_bias) and torch.equal(ma.fake_weight, mb.fake_weight)
+            assert float(ma.weight.detach().min()) == 1.0 and float(ma.running_mean.abs().max()) == 0.0
+    for ra, rb in zip(cal_a.relations, cal_b.relations):
+        assert torch.equal(ra.S, rb.S)
