@@ -282,8 +282,9 @@ class DeviceStack:
     @property
     def launches_per_step(self) -> int:
         """Kernels of this library per step: column-range reset + fold, equalization engine, correction engine
-        [+ range init, min/max, quantize]."""
-        return 4 + (3 if self.quant_plan is not None else 0)
+        [+ range init, min/max, quantize], plus the small copy kernel (k_copy_words) that moves each call's descriptor tables
+        (fold, equalization, correction [, quantize]) and the equalization's two result blocks through mapped pinned memory."""
+        return 4 + 5 + (4 if self.quant_plan is not None else 0)
 
 
 class HostStackCalibrator:
