@@ -84,6 +84,8 @@ struct ReadBack {
   }
   int enqueue(cudaStream_t st);   // 0 or an error code (message set)
   void finish();                  // after the stream has been synchronized
+  void abandon();                 // error paths: give the slot back without copying
+  ~ReadBack() { abandon(); }
 };
 
 // ------------------------------------------------------------------------------------------

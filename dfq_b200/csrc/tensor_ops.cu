@@ -100,6 +100,13 @@ void ReadBack::finish() {
   slot = -1;
 }
 
+void ReadBack::abandon() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_rb_mu);
+  g_rb[slot].busy = false;
+  slot = -1;
+}
+
 int TablePack::upload(cudaStream_t st) {
   dev = nullptr;
   if (total == 0) return 0;
