@@ -183,3 +183,54 @@ def test_two_rank_observer_sync(tmp_path):
     assert int(r0["n"]) == 3 and int(r1["n"]) == 3
     want = np.stack([np.minimum(r0["before"][:, 0], r1["before"][:, 0]), np.maximum(r0["before"][:, 1], r1["before"][:, 1])], axis=1)
     assert np.array_equal(r0["after"], want) and np.array_equal(r1["after"], want)
+
+
+class _TinyNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        self.c1 = nn.Conv2d(3, 6, 3, stride=4, padding=1, bias=False); self.b1 = nn.BatchNorm2d(6)
+        self.c2 = nn.Conv2d(6, 8, 3, stride=4, padding=1, bias=False); self.b2 = nn.BatchNorm2d(8)
+
+    def forward(self, x):
+        return self.b2(self.c2(torch.relu(self.b1(self.c1(x))))).mean((2, 3))
+
+
+def _tiny_net():
+    torch.manual_seed(3)
+    m = _TinyNet().eval()
+    for bn in (m.b1, m.b2):
+        bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+    return m
+
+
+def _distill_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dfq_b200 import distill
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        torch.manual_seed(99)
+        out = distill.getDistilData(_tiny_net(), "imagenet", 2, num_batch=3, gpu=False, value_range=[-2.5, 2.5], size=[224, 224],
+                                    early_break_factor=1e-9, iterations=3)
+        np.savez(os.path.join(out_dir, "distill%d.npz" % rank), **{"b%d" % i: t.numpy() for i, t in enumerate(out)})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_distilled_data_equals_one_process(tmp_path):
+    """getDistilData (ZeroQ/distill_data.py:75-227) with a process group: the batches are independent optimisations dealt
+    round-robin to the ranks; every rank draws the initial noise of ALL batches, so batch i starts where a single process
+    would have started it, and after the final broadcasts every rank holds the list one process would have produced."""
+    from dfq_b200 import distill
+    torch.manual_seed(99)
+    alone = distill.getDistilData(_tiny_net(), "imagenet", 2, num_batch=3, gpu=False, value_range=[-2.5, 2.5], size=[224, 224],
+                                  early_break_factor=1e-9, iterations=3)
+    port = 29500 + (os.getpid() % 2000) + 31
+    mp.spawn(_distill_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in (0, 1):
+        got = np.load(tmp_path / ("distill%d.npz" % rank))
+        for i, t in enumerate(alone):
+            assert np.array_equal(got["b%d" % i], t.numpy()), (rank, i)
